@@ -1,0 +1,67 @@
+"""In-tree build of libocean_b200.so (hand-written sm_100a kernels + the C ABI).
+
+    python -m gfx_ocean_b200.build [--force]
+
+nvcc cross-compiles for sm_100a without a GPU; the resulting .so sits next to this file, is
+git-ignored, and travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libocean_b200.so")
+SOURCES = ["ocean_api.cu", "kernels_literal.cu", "kernels_fused.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    # no --use_fast_math: the propagate phase needs the full-range sincosf (phases reach 1e3..1e4 rad)
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libocean_b200.so cannot be built (there is no CPU fallback)")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ocean_b200.h"), __file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    objs = []
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    for src in SOURCES:
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if verbose or r.returncode:
+            print(r.stdout)
+        if r.returncode:
+            raise RuntimeError(f"nvcc failed on {src}")
+        with open(obj + ".ptxas.log", "w") as f:
+            f.write(r.stdout)
+        objs.append(obj)
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        print(r.stdout)
+        raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,51 @@
+// Shared device helpers for the ocean kernels (sm_100a).
+//
+// Arithmetic contract: reference shaders under /root/reference/shader/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ocean {
+
+// `const float pi = 3.1415926;` (propagate.comp:6, fft_row.comp:5): rounds to 0x40490FDA.
+constexpr float kPi32 = 3.1415926f;
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex_mul of the shaders: (c0.x*c1.x - c0.y*c1.y, c0.y*c1.x + c0.x*c1.y)
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.y * b.x + a.x * b.y);
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+// propagate.comp:45-46,50-53. The shader forms `uint x = 2*gid - resolution - 1` in u32
+// (wraps for gid <= N/2) and converts it with an UNSIGNED int->float conversion
+// (OpConvertUToF in shader/spv/propagate.comp.spv), then k = pi * float(x) / domain_size.
+__device__ __forceinline__ float wave_number(uint32_t g, uint32_t n, float domain_size)
+{
+    const uint32_t u = 2u * g - n - 1u;
+    return __fdiv_rn(__fmul_rn(kPi32, __uint2float_rn(u)), domain_size);
+}
+
+// propagate.comp:64-67: k / length(k) if length(k) > 1e-10 else 0.
+__device__ __forceinline__ float2 unit_wave_vector(float kx, float ky)
+{
+    const float len = sqrtf(kx * kx + ky * ky);
+    float2 r = make_float2(0.f, 0.f);
+    if (len > 1.0e-10f) r = make_float2(kx / len, ky / len);
+    return r;
+}
+
+// propagate.comp:55-62: h = h0[idx]*(cos,sin)(w t) + h0[N*N-1-idx]*(cos,-sin)(w t).
+// The phase product is fp32 (it reaches thousands of radians), the sincos is the
+// full-range accurate one: never compile this file with --use_fast_math.
+__device__ __forceinline__ float2 propagate_point(float2 a, float2 b, float omega, float time)
+{
+    float s, c;
+    sincosf(__fmul_rn(omega, time), &s, &c);
+    // (a.x c - a.y s) + (b.x c + b.y s),  (a.y c + a.x s) + (b.y c - b.x s)
+    return make_float2((a.x + b.x) * c - (a.y - b.y) * s, (a.y + b.y) * c + (a.x - b.x) * s);
+}
+
+}  // namespace ocean

@@ -1,0 +1,150 @@
+/*
+ * ocean_b200.h -- C ABI of the B200-native ocean-surface synthesiser.
+ *
+ * Drop-in boundary for the per-frame compute path of gfx-rs/gfx-ocean
+ *     propagate -> fft_row x3 -> fft_col x3 -> correction
+ * which the reference records inline in Renderer::render()
+ * (src/render.rs:1101-1310) through three operator holders:
+ *     Propagation<B>  src/ocean.rs:15-177   (uniform PropagateLocals :8-13)
+ *     Fft<B>          src/fft.rs:7-111
+ *     Correction<B>   src/ocean.rs:184-328  (uniform CorrectionLocals :179-182)
+ * The reference has no FFI for this path (its only extern "C" is the iOS
+ * launcher, examples/ios/ios.rs:3-6); this header is what a Rust `extern "C"`
+ * block would bind (bindings/rust/ocean.rs).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns an ocean_status
+ *    (0 = OK, negative = error) and never throws or aborts across the boundary
+ *    (the reference's `Result<_, Box<dyn Error>>` / unwrap() convention,
+ *    src/fft.rs:19, src/render.rs:1078, mapped to codes + ocean_last_error()).
+ *  - one context = one CUDA device + one stream; a context is not thread-safe
+ *    (the reference drives everything from the winit thread, src/lib.rs:105-170).
+ *  - grid point (x, y) lives at index x + N*y, x fastest (propagate.comp:43).
+ *  - there is NO CPU fallback: without a CUDA device ocean_create fails with
+ *    OCEAN_ERR_NO_DEVICE.
+ */
+#ifndef OCEAN_B200_H
+#define OCEAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCEAN_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define OCEAN_API __attribute__((visibility("default")))
+#else
+#define OCEAN_API
+#endif
+
+typedef struct ocean_ctx ocean_ctx;
+
+typedef enum ocean_status {
+    OCEAN_OK = 0,
+    OCEAN_ERR_INVALID_ARG = -1, /* null pointer, tile out of range, N not a supported power of two */
+    OCEAN_ERR_NO_DEVICE = -2,   /* no CUDA device / device index out of range / not sm_100 */
+    OCEAN_ERR_CUDA = -3,        /* a CUDA runtime call failed; see ocean_last_error */
+    OCEAN_ERR_IO = -4,          /* bincode file missing, truncated or of the wrong size */
+    OCEAN_ERR_NOT_READY = -5,   /* update/download before every tile has a spectrum */
+    OCEAN_ERR_UNSUPPORTED = -6  /* option not available in this build */
+} ocean_status;
+
+/* Which kernels ocean_update enqueues. Both produce the same displacement map. */
+typedef enum ocean_pipeline {
+    /* The product path: two fused sm_100a kernels per frame (propagate + row
+     * transforms; column transforms + sign correction + RGBA pack). */
+    OCEAN_PIPELINE_FUSED = 0,
+    /* The reference's own dataflow kept for A/B measurement: 4 kernels, 8
+     * launches, radix-2 Stockham in shared memory, per-butterfly sincos
+     * (src/render.rs:1122-1287 recompiled for sm_100a). */
+    OCEAN_PIPELINE_LITERAL = 1
+} ocean_pipeline;
+
+/* Mirrors of the reference's uniform blocks (std430, 4-byte scalars). */
+typedef struct ocean_propagate_locals { /* src/ocean.rs:8-13, propagate.comp:16-20 */
+    float   time;
+    int32_t resolution;
+    float   domain_size;
+} ocean_propagate_locals;
+
+typedef struct ocean_correction_locals { /* src/ocean.rs:179-182, correction.comp:6-8 (never read there) */
+    uint32_t resolution;
+} ocean_correction_locals;
+
+typedef struct ocean_config {
+    uint32_t abi_version;   /* OCEAN_B200_ABI_VERSION */
+    int32_t  cuda_device;   /* ordinal */
+    uint32_t resolution;    /* N: power of two, 8 <= N <= 4096 (reference: RESOLUTION = 512, src/render.rs:44) */
+    float    domain_size;   /* L (reference: DOMAIN_SIZE = 1000.0, src/render.rs:46); output-invariant */
+    uint32_t n_tiles;       /* independent oceans held by this context, >= 1 */
+    uint32_t pipeline;      /* ocean_pipeline */
+    void*    stream;        /* cudaStream_t to enqueue on, or NULL to let the context create one */
+    uint32_t flags;         /* OCEAN_FLAG_* */
+} ocean_config;
+
+#define OCEAN_FLAG_NONE          0u
+#define OCEAN_FLAG_KEEP_SPECTRA  1u  /* LITERAL pipeline keeps post-propagate spectra for ocean_debug_spectra */
+
+/* ---- lifetime (Propagation/Fft/Correction::init + Renderer::new buffers, src/render.rs:223-225,607-729) */
+OCEAN_API int  ocean_create(ocean_ctx** out, int cuda_device, uint32_t resolution, float domain_size, uint32_t n_tiles);
+OCEAN_API int  ocean_create_ex(ocean_ctx** out, const ocean_config* cfg);
+OCEAN_API void ocean_destroy(ocean_ctx* ctx);            /* ::destroy(), src/fft.rs:102, src/ocean.rs:170,321 */
+
+/* ---- inputs (staging upload of data/omega.bin + data/spectrum.bin, src/render.rs:742-931) */
+/* h0_xy: N*N*2 floats (re, im interleaved); omega: N*N floats. Host pointers; copied before return. */
+OCEAN_API int  ocean_set_spectrum(ocean_ctx* ctx, uint32_t tile, const float* h0_xy, const float* omega);
+/* Same, device pointers on the context's device; copied on the context's stream. */
+OCEAN_API int  ocean_set_spectrum_device(ocean_ctx* ctx, uint32_t tile, const float* d_h0_xy, const float* d_omega);
+/* bincode Vec<f32> / Vec<[f32;2]> files as shipped by the reference (src/render.rs:769-771,808-810). */
+OCEAN_API int  ocean_load_bincode(ocean_ctx* ctx, uint32_t tile, const char* omega_path, const char* spectrum_path);
+
+/* ---- the hot path (src/render.rs:1101-1310 steps 2-10) */
+/* Enqueue one frame for every tile: writes PropagateLocals{time, resolution, domain_size}
+ * and runs propagate -> 2-D inverse transform of (dx, height, dz) -> correction. Asynchronous. */
+OCEAN_API int  ocean_update(ocean_ctx* ctx, float time);
+/* Same for tiles [first_tile, first_tile + count). */
+OCEAN_API int  ocean_update_tiles(ocean_ctx* ctx, float time, uint32_t first_tile, uint32_t count);
+/* Enqueue `n_frames` consecutive updates at times t0 + i*dt (host loop inside the library). */
+OCEAN_API int  ocean_update_sequence(ocean_ctx* ctx, float t0, float dt, uint32_t n_frames);
+
+/* ---- outputs (the RGBA32F displacement_map, src/render.rs:820-845; texel = (dx, height, dz, 0)) */
+/* Device pointer to tile's N*N*4 floats, row-major [y][x][4]; stable until ocean_destroy. */
+OCEAN_API int  ocean_output_device(ocean_ctx* ctx, uint32_t tile, const float** d_rgba);
+/* Copy tile's output to host memory (N*N*4 floats). Waits for the stream. */
+OCEAN_API int  ocean_download(ocean_ctx* ctx, uint32_t tile, float* h_rgba);
+/* Enqueue the copy only (h_rgba should be page-locked); pair with ocean_sync. */
+OCEAN_API int  ocean_download_async(ocean_ctx* ctx, uint32_t tile, float* h_rgba);
+OCEAN_API int  ocean_sync(ocean_ctx* ctx);
+
+/* ---- measurement */
+/* One update with CUDA events recorded on the context's stream around every kernel of the frame;
+ * waits, then writes each kernel's duration in ms (FUSED: [k_rows, k_cols]; LITERAL: the 8
+ * dispatches in reference order). *n_stages receives the count; capacity is stage_ms's length. */
+OCEAN_API int  ocean_profile_update(ocean_ctx* ctx, float time, float* stage_ms, uint32_t capacity, uint32_t* n_stages);
+
+/* ---- introspection */
+/* Post-propagate spectra of a tile (N*N*2 floats each, host), recomputed at the time of the
+ * last update with the standalone propagate kernel. Parity/debug only; waits for the stream. */
+OCEAN_API int  ocean_debug_spectra(ocean_ctx* ctx, uint32_t tile, float* h, float* dx, float* dz);
+/* The uniform blocks as last written by ocean_update (what the reference maps at src/render.rs:1101-1120). */
+OCEAN_API int  ocean_get_locals(const ocean_ctx* ctx, ocean_propagate_locals* p, ocean_correction_locals* c);
+OCEAN_API uint32_t ocean_resolution(const ocean_ctx* ctx);
+OCEAN_API uint32_t ocean_n_tiles(const ocean_ctx* ctx);
+/* Kernel launches enqueued by this context since creation (for gpu_launches accounting). */
+OCEAN_API uint64_t ocean_launch_count(const ocean_ctx* ctx);
+/* The stream the context enqueues on (cudaStream_t as void*). */
+OCEAN_API void* ocean_stream(const ocean_ctx* ctx);
+/* Algorithmic bytes one ocean_update moves: 76 * N*N * n_tiles. */
+OCEAN_API uint64_t ocean_algorithmic_bytes_per_update(const ocean_ctx* ctx);
+/* Message of the last error on this context ("" if none); ctx may be NULL for create-time errors. */
+OCEAN_API const char* ocean_last_error(const ocean_ctx* ctx);
+OCEAN_API const char* ocean_status_string(int status);
+OCEAN_API uint32_t ocean_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCEAN_B200_H */
