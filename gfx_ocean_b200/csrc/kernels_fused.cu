@@ -62,7 +62,8 @@ __device__ __forceinline__ float2 rot_mul_conj(float4 s)
 template <int N, int P, int PAIRS>
 __global__ void __launch_bounds__(3 * PAIRS * (N / P))
 k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, const float2* __restrict__ tw_g,
-       float2* __restrict__ gp_all, float2* __restrict__ gh_all, float time, float domain_size, uint32_t first_tile)
+       const float* __restrict__ kx_g, float2* __restrict__ gp_all, float2* __restrict__ gh_all, float time,
+       uint32_t first_tile)
 {
     using Cfg = LineCfg<N, P>;
     constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2;
@@ -71,8 +72,8 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* S = reinterpret_cast<float4*>(smem_raw);                     // [NROWS][N]  (h.re, h.im, khat.x, khat.z)
-    float2* TW = reinterpret_cast<float2*>(S + NROWS * N);               // [R1][R2]    w_N^(n1 k2)
-    float2* X = TW + N;                                                  // [3 PAIRS][LINE]
+    float2* X = reinterpret_cast<float2*>(smem_raw);                     // [3 PAIRS][LINE], reuses S after phase B's loads
+    static_assert(sizeof(float2) * 3 * PAIRS * Cfg::LINE <= sizeof(float4) * NROWS * N, "exchange lines must fit in S");
 
     const uint32_t tile = first_tile + blockIdx.y;
     const float2* __restrict__ h0 = h0_all + size_t(tile) * N * N;
@@ -83,20 +84,20 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
     const int tid = threadIdx.x;
 
     // ---- phase A: propagate.comp for the block's 2*PAIRS rows -> shared memory
-    for (int i = tid; i < N; i += NT) TW[i] = tw_g[i];
     auto row_of = [&](int slot) -> uint32_t {
         const uint32_t j = blockIdx.x * PAIRS + (slot >> 1);             // pair index, 0 = the self-paired rows
         if (j == 0) return (slot & 1) ? N / 2 : 0;
         return (slot & 1) ? N - j : j;
     };
-#pragma unroll 4
+#pragma unroll 8
     for (int i = tid; i < NROWS * N; i += NT) {
         const int slot = i / N;
         const uint32_t x = i % N, r = row_of(slot);
         const uint32_t index = x + N * r;                                // propagate.comp:43
         const uint32_t index_neg = (N - r - 1u) * N + N - x - 1u;        // :48
         const float2 h = propagate_point(__ldg(h0 + index), __ldg(h0 + index_neg), __ldg(omega + index), time);
-        const float2 kh = unit_wave_vector(wave_number(x, N, domain_size), wave_number(r, N, domain_size));
+        // kx_g[g] = pi32 * float(uint(2g - N - 1)) / L, tabulated on the host with the shader's fp32 ops
+        const float2 kh = unit_wave_vector_fast(__ldg(kx_g + x), __ldg(kx_g + r));
         S[slot * N + x] = make_float4(h.x, h.y, kh.x, kh.y);
     }
     __syncthreads();
@@ -138,10 +139,11 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
             }
         }
     }
+    __syncthreads();                      // every warp has its inputs: S may be overwritten by the lines
     RegFft<R1>::run(v);
 #pragma unroll
     for (int n1 = 0; n1 < R1; ++n1) {
-        const float2 y = n1 == 0 ? v[0] : cmul_tw(v[n1], TW[n1 * R2 + k2]);
+        const float2 y = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * R2 + k2));
         line[Cfg::pad(n1 * R2 + k2)] = y;
     }
     __syncwarp();
@@ -170,7 +172,7 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
 // k_cols
 // ------------------------------------------------------------------------------------------
 template <int N, int P, int C>
-__global__ void __launch_bounds__(3 * C * (N / P) / 2)
+__global__ void __launch_bounds__(3 * C * (N / P) / 2, 2)
 k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, const float2* __restrict__ tw_g,
        float4* __restrict__ out_all, uint32_t first_tile)
 {
@@ -181,10 +183,10 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
     constexpr int NT = NTP + HC * T;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* TW = reinterpret_cast<float2*>(smem_raw);      // [R1][R2]
-    float2* XP = TW + N;                                   // [C][LINE]
+    float2* XP = reinterpret_cast<float2*>(smem_raw);      // [C][LINE]
     float2* XH = XP + C * LINE;                            // [C/2][LINE]
-    float* HR = reinterpret_cast<float*>(XH + HC * LINE);  // [N][C] height results
+    float* HR = reinterpret_cast<float*>(XH);              // [N][C] height results, reuses XH once it is consumed
+    static_assert(sizeof(float) * N * C <= sizeof(float2) * HC * LINE, "height results must fit in XH");
 
     const float2* __restrict__ gp = gp_all + size_t(blockIdx.y) * N * N;
     const float2* __restrict__ gh = gh_all + size_t(blockIdx.y) * (N / 2) * N;
@@ -192,7 +194,6 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
 
     const int tid = threadIdx.x;
     const uint32_t n0 = blockIdx.x * C;
-    for (int i = tid; i < N; i += NT) TW[i] = tw_g[i];
 
     const bool is_p = tid < NTP;
     // lanes run over columns first so that a warp's loads cover whole 32/64-byte row segments
@@ -221,11 +222,10 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
             v[k1] = z;
         }
     }
-    __syncthreads();                      // TW visible
     RegFft<R1>::run(v);
 #pragma unroll
     for (int n1 = 0; n1 < R1; ++n1) {
-        const float2 y = n1 == 0 ? v[0] : cmul_tw(v[n1], TW[n1 * R2 + k2]);
+        const float2 y = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * R2 + k2));
         line[Cfg::pad(n1 * R2 + k2)] = y;
     }
     __syncthreads();
@@ -237,6 +237,12 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
         const int n1 = k2 + R2 * i;
 #pragma unroll
         for (int k = 0; k < R2; ++k) u[i][k] = line[Cfg::pad(n1 * R2 + k)];
+    }
+    // the height threads have drained XH; only they need to agree before HR overwrites it
+    if (!is_p) asm volatile("bar.sync 1, %0;" ::"n"(HC * T) : "memory");
+#pragma unroll
+    for (int i = 0; i < Cfg::SUB2; ++i) {
+        const int n1 = k2 + R2 * i;
         RegFft<R2>::run(u[i]);
         if (!is_p) {                      // height columns: park the two real results for the packers
 #pragma unroll
@@ -270,6 +276,7 @@ struct FusedPlan {
     uint32_t n = 0, n_tiles = 0;
     float domain_size = 0.f;
     float2* d_tw = nullptr;      // [R1][R2] inter-pass twiddles
+    float* d_kx = nullptr;       // [N] wave numbers, propagate.comp:45-46,50-53
     float2* d_gp = nullptr;      // [tiles][N][N]
     float2* d_gh = nullptr;      // [tiles][N/2][N]
 };
@@ -277,8 +284,8 @@ struct FusedPlan {
 template <int N, int P, int PAIRS, int C>
 struct Launch {
     using Cfg = LineCfg<N, P>;
-    static constexpr size_t smem_rows = sizeof(float4) * 2 * PAIRS * N + sizeof(float2) * N + sizeof(float2) * 3 * PAIRS * Cfg::LINE;
-    static constexpr size_t smem_cols = sizeof(float2) * N + sizeof(float2) * (C + C / 2) * Cfg::LINE + sizeof(float) * N * C;
+    static constexpr size_t smem_rows = sizeof(float4) * 2 * PAIRS * N;
+    static constexpr size_t smem_cols = sizeof(float2) * (C + C / 2) * Cfg::LINE;
 
     static cudaError_t prepare()
     {
@@ -292,8 +299,8 @@ struct Launch {
     {
         if (ev) cudaEventRecord(ev[0], s);
         const dim3 grid_rows(N / 2 / PAIRS, count), grid_cols(N / C, count);
-        k_rows<N, P, PAIRS><<<grid_rows, 3 * PAIRS * Cfg::T, smem_rows, s>>>(h0, omega, p->d_tw, p->d_gp, p->d_gh, time,
-                                                                             p->domain_size, first_tile);
+        k_rows<N, P, PAIRS><<<grid_rows, 3 * PAIRS * Cfg::T, smem_rows, s>>>(h0, omega, p->d_tw, p->d_kx, p->d_gp, p->d_gh,
+                                                                             time, first_tile);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (ev) cudaEventRecord(ev[1], s);
@@ -341,6 +348,15 @@ cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, flo
         }
     if ((e = cudaMalloc(&p->d_tw, n * sizeof(float2))) != cudaSuccess) return bail(e);
     if ((e = cudaMemcpy(p->d_tw, tw.data(), n * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
+    // the shader's fp32 arithmetic, op for op: k = pi * float(uint(2g - N - 1)) / domain_size
+    std::vector<float> kx(n);
+    for (uint32_t g = 0; g < n; ++g) {
+        const uint32_t u = 2u * g - n - 1u;
+        volatile float prod = kPi32 * float(u);
+        kx[g] = prod / domain_size;
+    }
+    if ((e = cudaMalloc(&p->d_kx, n * sizeof(float))) != cudaSuccess) return bail(e);
+    if ((e = cudaMemcpy(p->d_kx, kx.data(), n * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
     const size_t np = size_t(n) * n;
     if ((e = cudaMalloc(&p->d_gp, size_t(n_tiles) * np * sizeof(float2))) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc(&p->d_gh, size_t(n_tiles) * (np / 2) * sizeof(float2))) != cudaSuccess) return bail(e);
@@ -358,6 +374,7 @@ void fused_plan_destroy(FusedPlan* p)
 {
     if (!p) return;
     cudaFree(p->d_tw);
+    cudaFree(p->d_kx);
     cudaFree(p->d_gp);
     cudaFree(p->d_gh);
     delete p;

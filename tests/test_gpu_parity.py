@@ -76,7 +76,7 @@ def test_debug_spectra_match_oracle_propagate(shipped_fused, oracle, ref_inputs)
         for a, b in ((h, rh), (dx, rdx), (dz, rdz)):
             assert np.abs(a - b).max() / np.abs(b).max() <= 2e-6
     np.testing.assert_allclose(dx[300, 200], -1j * h[300, 200], rtol=1e-6)
-    assert abs(dz[300, 200]) < 1e-9 * abs(h[300, 200]) + 1e-12
+    assert abs(dz[300, 200]) < 1e-7 * abs(h[300, 200])          # khat.z ~ 2e-8 where only gx is wrapped
 
 
 def test_fused_and_literal_agree(shipped_fused, shipped_literal):
