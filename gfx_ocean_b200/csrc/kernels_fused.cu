@@ -59,8 +59,8 @@ __device__ __forceinline__ float2 rot_mul_conj(float4 s)
     return make_float2(fmaf(s.w, s.x, -s.z * s.y), -fmaf(s.w, s.y, s.z * s.x));
 }
 
-template <int N, int P, int PAIRS>
-__global__ void __launch_bounds__(3 * PAIRS * (N / P))
+template <int N, int P, int PAIRS, int MINB>
+__global__ void __launch_bounds__(3 * PAIRS * (N / P), MINB)
 k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, const float2* __restrict__ tw_g,
        const float* __restrict__ kx_g, float2* __restrict__ gp_all, float2* __restrict__ gh_all, float time,
        uint32_t first_tile)
@@ -69,11 +69,12 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
     constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2;
     constexpr int NT = 3 * PAIRS * T;
     constexpr int NROWS = 2 * PAIRS;
+    constexpr int SP = N + 1;             // row pitch of S: element N duplicates element 0, so S[N - x] is -x mod N
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* S = reinterpret_cast<float4*>(smem_raw);                     // [NROWS][N]  (h.re, h.im, khat.x, khat.z)
+    float4* S = reinterpret_cast<float4*>(smem_raw);                     // [NROWS][N+1]  (h.re, h.im, khat.x, khat.z)
     float2* X = reinterpret_cast<float2*>(smem_raw);                     // [3 PAIRS][LINE], reuses S after phase B's loads
-    static_assert(sizeof(float2) * 3 * PAIRS * Cfg::LINE <= sizeof(float4) * NROWS * N, "exchange lines must fit in S");
+    static_assert(sizeof(float2) * 3 * PAIRS * Cfg::LINE <= sizeof(float4) * NROWS * SP, "exchange lines must fit in S");
 
     const uint32_t tile = first_tile + blockIdx.y;
     const float2* __restrict__ h0 = h0_all + size_t(tile) * N * N;
@@ -83,22 +84,51 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
 
     const int tid = threadIdx.x;
 
-    // ---- phase A: propagate.comp for the block's 2*PAIRS rows -> shared memory
-    auto row_of = [&](int slot) -> uint32_t {
-        const uint32_t j = blockIdx.x * PAIRS + (slot >> 1);             // pair index, 0 = the self-paired rows
-        if (j == 0) return (slot & 1) ? N / 2 : 0;
-        return (slot & 1) ? N - j : j;
-    };
-#pragma unroll 8
-    for (int i = tid; i < NROWS * N; i += NT) {
-        const int slot = i / N;
-        const uint32_t x = i % N, r = row_of(slot);
-        const uint32_t index = x + N * r;                                // propagate.comp:43
-        const uint32_t index_neg = (N - r - 1u) * N + N - x - 1u;        // :48
-        const float2 h = propagate_point(__ldg(h0 + index), __ldg(h0 + index_neg), __ldg(omega + index), time);
-        // kx_g[g] = pi32 * float(uint(2g - N - 1)) / L, tabulated on the host with the shader's fp32 ops
-        const float2 kh = unit_wave_vector_fast(__ldg(kx_g + x), __ldg(kx_g + r));
-        S[slot * N + x] = make_float4(h.x, h.y, kh.x, kh.y);
+    // ---- phase A: propagate.comp for the block's 2*PAIRS rows -> shared memory.
+    // Two adjacent points per step (128-bit loads), UB steps batched so their loads are in flight together.
+    {
+        constexpr int NPAIR = NROWS * N / 2;
+        constexpr int ITER = (NPAIR + NT - 1) / NT;
+        constexpr int UB = 4;
+#pragma unroll 1
+        for (int it0 = 0; it0 < ITER; it0 += UB) {
+            float4 a[UB], b[UB];
+            float2 w[UB], kx[UB];
+            float ky[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int i = tid + (it0 + u) * NT;
+                const bool valid = (it0 + u < ITER) && i < NPAIR;
+                const int slot = valid ? i / (N / 2) : 0;
+                const uint32_t x = valid ? 2 * (i % (N / 2)) : 0;
+                const uint32_t jp = blockIdx.x * PAIRS + (slot >> 1);    // pair index, 0 = the self-paired rows 0, N/2
+                const uint32_t r = jp == 0 ? ((slot & 1) ? N / 2 : 0) : ((slot & 1) ? N - jp : jp);
+                const uint32_t index = x + N * r;                        // propagate.comp:43
+                const uint32_t index_neg = (N - r - 1u) * N + N - x - 2u;   // :48 for x+1; the partner of x is one further
+                a[u] = __ldg(reinterpret_cast<const float4*>(h0 + index));
+                b[u] = __ldg(reinterpret_cast<const float4*>(h0 + index_neg));
+                w[u] = __ldg(reinterpret_cast<const float2*>(omega + index));
+                // kx_g[g] = pi32 * float(uint(2g - N - 1)) / L, tabulated on the host with the shader's fp32 ops
+                kx[u] = __ldg(reinterpret_cast<const float2*>(kx_g + x));
+                ky[u] = __ldg(kx_g + r);
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int i = tid + (it0 + u) * NT;
+                if ((it0 + u < ITER) && i < NPAIR) {
+                    const int slot = i / (N / 2);
+                    const uint32_t x = 2 * (i % (N / 2));
+                    const float2 h_0 = propagate_point_fast(make_float2(a[u].x, a[u].y), make_float2(b[u].z, b[u].w), w[u].x, time);
+                    const float2 h_1 = propagate_point_fast(make_float2(a[u].z, a[u].w), make_float2(b[u].x, b[u].y), w[u].y, time);
+                    const float2 k_0 = unit_wave_vector_fast(kx[u].x, ky[u]);
+                    const float2 k_1 = unit_wave_vector_fast(kx[u].y, ky[u]);
+                    float4* row = S + slot * SP;
+                    row[x] = make_float4(h_0.x, h_0.y, k_0.x, k_0.y);
+                    row[x + 1] = make_float4(h_1.x, h_1.y, k_1.x, k_1.y);
+                    if (x == 0) row[N] = make_float4(h_0.x, h_0.y, k_0.x, k_0.y);
+                }
+            }
+        }
     }
     __syncthreads();
 
@@ -108,35 +138,44 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
     const int k2 = tid % T;
     const uint32_t j = blockIdx.x * PAIRS + pair;
     const bool self_paired = (j == 0);
-    const float4* S0 = S + (2 * pair) * N;
-    const float4* S1 = S0 + N;
+    const float4* S0 = S + (2 * pair) * SP;
+    const float4* S1 = S0 + SP;
     float2* line = X + f * Cfg::LINE;
 
     float2 v[R1];
+    if (seq < 2) {
+        // P_S(A; B) = (b_A - i a_A) h_A - (b_B - i a_B) conj(h_B), kh = (a, b):
+        //   seq 0: A = (x, y),    B = (-x, N-y)   -> row y of GP
+        //   seq 1: A = (-x, N-y), B = (x, y)      -> row N-y of GP, transformed and stored mirrored
+        //   rows 0 and N/2 are their own partners: A = (x, r), B = (-x, r), natural order
+        const bool mirror_a = !self_paired && seq == 1;
+        const float4* PA = (seq == 0) ? S0 : S1;
+        const float4* PB = self_paired ? PA : (seq == 0 ? S1 : S0);
+        // element k1: x = k1 R2 + k2; A at (mirror_a ? N - x : x), B at the other one
+        const int step = mirror_a ? -R2 : R2;
+        const float4* pa = PA + (mirror_a ? N - k2 : k2);
+        const float4* pb = PB + (mirror_a ? k2 : N - k2);
 #pragma unroll
-    for (int k1 = 0; k1 < R1; ++k1) {
-        const uint32_t x = k1 * R2 + k2;
-        const uint32_t nx = (N - x) & (N - 1);
-        if (!self_paired) {
-            const float4 A = S0[x], B = S1[nx];      // A = (x, y), B = (-x, N-y)
-            if (seq == 0) {                          // P_S(x, y)
-                const float2 qa = rot_mul(A), qb = rot_mul_conj(B);
-                v[k1] = make_float2(qa.x - qb.x, qa.y - qb.y);
-            } else if (seq == 1) {                   // P_S(-x, N-y): transformed mirrored, stored mirrored
-                const float2 qa = rot_mul(B), qb = rot_mul_conj(A);
-                v[k1] = make_float2(qa.x - qb.x, qa.y - qb.y);
-            } else {                                 // h_S(x, y)
-                v[k1] = make_float2(A.x + B.x, A.y - B.y);
-            }
-        } else {                                     // rows 0 and N/2 are their own partners
-            if (seq < 2) {
-                const float4* Sr = seq == 0 ? S0 : S1;
-                const float2 qa = rot_mul(Sr[x]), qb = rot_mul_conj(Sr[nx]);
-                v[k1] = make_float2(qa.x - qb.x, qa.y - qb.y);
-            } else {                                 // h_S(x, 0) + i h_S(x, N/2): both transforms are real
-                const float4 a0 = S0[x], b0 = S0[nx], a1 = S1[x], b1 = S1[nx];
-                v[k1] = make_float2((a0.x + b0.x) - (a1.y - b1.y), (a0.y - b0.y) + (a1.x + b1.x));
-            }
+        for (int k1 = 0; k1 < R1; ++k1) {
+            const float2 qa = rot_mul(pa[k1 * step]), qb = rot_mul_conj(pb[-k1 * step]);
+            v[k1] = make_float2(qa.x - qb.x, qa.y - qb.y);
+        }
+    } else if (!self_paired) {
+        // h_S(x, y) = h(x, y) + conj h(-x, N-y)
+        const float2* pa = reinterpret_cast<const float2*>(S0 + k2);
+        const float2* pb = reinterpret_cast<const float2*>(S1 + N - k2);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            const float2 A = pa[2 * k1 * R2], B = pb[-2 * k1 * R2];
+            v[k1] = make_float2(A.x + B.x, A.y - B.y);
+        }
+    } else {
+        // h_S(x, 0) + i h_S(x, N/2): both row transforms are real, so they share one complex transform
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            const int x = k1 * R2 + k2;
+            const float4 a0 = S0[x], b0 = S0[N - x], a1 = S1[x], b1 = S1[N - x];
+            v[k1] = make_float2((a0.x + b0.x) - (a1.y - b1.y), (a0.y - b0.y) + (a1.x + b1.x));
         }
     }
     __syncthreads();                      // every warp has its inputs: S may be overwritten by the lines
@@ -150,7 +189,7 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
 
     float2* dst;
     bool mirrored = false;
-    if (seq == 0) dst = gp + size_t(self_paired ? 0 : j) * N;
+    if (seq == 0) dst = gp + size_t(j) * N;
     else if (seq == 1) { dst = gp + size_t(self_paired ? N / 2 : N - j) * N; mirrored = !self_paired; }
     else dst = gh + size_t(j) * N;
 #pragma unroll
@@ -180,7 +219,6 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
     constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2, LINE = Cfg::LINE;
     constexpr int NTP = C * T;            // threads on the packed (dx, dz) columns
     constexpr int HC = C / 2;             // packed height columns
-    constexpr int NT = NTP + HC * T;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* XP = reinterpret_cast<float2*>(smem_raw);      // [C][LINE]
@@ -281,15 +319,15 @@ struct FusedPlan {
     float2* d_gh = nullptr;      // [tiles][N/2][N]
 };
 
-template <int N, int P, int PAIRS, int C>
+template <int N, int P, int PAIRS, int C, int MINB>
 struct Launch {
     using Cfg = LineCfg<N, P>;
-    static constexpr size_t smem_rows = sizeof(float4) * 2 * PAIRS * N;
+    static constexpr size_t smem_rows = sizeof(float4) * 2 * PAIRS * (N + 1);
     static constexpr size_t smem_cols = sizeof(float2) * (C + C / 2) * Cfg::LINE;
 
     static cudaError_t prepare()
     {
-        cudaError_t e = cudaFuncSetAttribute(k_rows<N, P, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_rows));
+        cudaError_t e = cudaFuncSetAttribute(k_rows<N, P, PAIRS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_rows));
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(k_cols<N, P, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cols));
     }
@@ -299,7 +337,7 @@ struct Launch {
     {
         if (ev) cudaEventRecord(ev[0], s);
         const dim3 grid_rows(N / 2 / PAIRS, count), grid_cols(N / C, count);
-        k_rows<N, P, PAIRS><<<grid_rows, 3 * PAIRS * Cfg::T, smem_rows, s>>>(h0, omega, p->d_tw, p->d_kx, p->d_gp, p->d_gh,
+        k_rows<N, P, PAIRS, MINB><<<grid_rows, 3 * PAIRS * Cfg::T, smem_rows, s>>>(h0, omega, p->d_tw, p->d_kx, p->d_gp, p->d_gh,
                                                                              time, first_tile);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -311,9 +349,9 @@ struct Launch {
     }
 };
 
-using L256 = Launch<256, 16, 2, 8>;
-using L512 = Launch<512, 32, 2, 8>;
-using L1024 = Launch<1024, 32, 1, 8>;
+using L256 = Launch<256, 16, 2, 8, 4>;
+using L512 = Launch<512, 32, 2, 8, 4>;
+using L1024 = Launch<1024, 32, 1, 8, 6>;
 
 bool fused_supports(uint32_t n) { return n == 256 || n == 512 || n == 1024; }
 

@@ -37,7 +37,7 @@ def shipped_literal():
         yield o
 
 
-@pytest.mark.parametrize("t", [0.0, 1.0, 37.5, 600.0])
+@pytest.mark.parametrize("t", [0.0, 1.0, 37.5, 600.0, 25000.0])   # 25000 s: phases > 1e5 rad (slow sincos path)
 @pytest.mark.parametrize("which", ["fused", "literal"])
 def test_shipped_data_matches_oracle(which, t, shipped_fused, shipped_literal, oracle, ref_inputs):
     """BASELINE.json config 2: the reference's own data/omega.bin + data/spectrum.bin at N=512."""
