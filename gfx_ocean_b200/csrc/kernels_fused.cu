@@ -45,6 +45,24 @@ struct LineCfg {
     static constexpr int LINE = ((pad(N - 1) + 1 - 2 + 15) / 16) * 16 + 2;
 };
 
+// Layout of the row-pass output in HBM/L2 (ours to choose: nothing outside the two kernels sees it).
+// Strip-major: all rows of the C columns [s*C, (s+1)*C) are contiguous, so the column pass pulls its
+// whole working set with ONE bulk copy; inside a strip rows are grouped by GS = R2 with one pad row
+// per group, which is exactly the shared-memory image the in-place column transform wants
+// (group pitch = 64 (mod 128) bytes for C = 8: pass-2 reads of neighbouring groups hit disjoint banks).
+//   GP: N rows (packed dx/dz field)      GH: N/2 rows (height field, row 0 = rows 0 and N/2 packed)
+template <int N, int C, int GS>
+struct Inter {
+    static constexpr int GROUP_PITCH = (GS + 1) * C;                     // float2 per row group
+    static constexpr int P_STRIP = (N / GS) * GROUP_PITCH;               // float2 per strip of GP
+    static constexpr int H_STRIP = (N / 2 / GS) * GROUP_PITCH;           // float2 per strip of GH
+    static constexpr size_t P_TILE = size_t(P_STRIP) * (N / C);
+    static constexpr size_t H_TILE = size_t(H_STRIP) * (N / C);
+    __host__ __device__ static constexpr uint32_t row_off(uint32_t y) { return (y / GS) * GROUP_PITCH + (y % GS) * C; }
+    __host__ __device__ static constexpr size_t p_off(uint32_t y, uint32_t n) { return size_t(n / C) * P_STRIP + row_off(y) + n % C; }
+    __host__ __device__ static constexpr size_t h_off(uint32_t y, uint32_t n) { return size_t(n / C) * H_STRIP + row_off(y) + n % C; }
+};
+
 // ------------------------------------------------------------------------------------------
 // k_rows
 // ------------------------------------------------------------------------------------------
@@ -59,7 +77,7 @@ __device__ __forceinline__ float2 rot_mul_conj(float4 s)
     return make_float2(fmaf(s.w, s.x, -s.z * s.y), -fmaf(s.w, s.y, s.z * s.x));
 }
 
-template <int N, int P, int PAIRS, int MINB>
+template <int N, int P, int PAIRS, int C, int MINB>
 __global__ void __launch_bounds__(3 * PAIRS * (N / P), MINB)
 k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, const float2* __restrict__ tw_g,
        const float* __restrict__ kx_g, float2* __restrict__ gp_all, float2* __restrict__ gh_all, float time,
@@ -79,54 +97,49 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
     const uint32_t tile = first_tile + blockIdx.y;
     const float2* __restrict__ h0 = h0_all + size_t(tile) * N * N;
     const float* __restrict__ omega = omega_all + size_t(tile) * N * N;
-    float2* __restrict__ gp = gp_all + size_t(blockIdx.y) * N * N;
-    float2* __restrict__ gh = gh_all + size_t(blockIdx.y) * (N / 2) * N;
+    using IL = Inter<N, C, Cfg::R2>;
+    float2* __restrict__ gp = gp_all + size_t(blockIdx.y) * IL::P_TILE;
+    float2* __restrict__ gh = gh_all + size_t(blockIdx.y) * IL::H_TILE;
 
     const int tid = threadIdx.x;
 
     // ---- phase A: propagate.comp for the block's 2*PAIRS rows -> shared memory.
-    // Two adjacent points per step (128-bit loads), UB steps batched so their loads are in flight together.
-    {
-        constexpr int NPAIR = NROWS * N / 2;
-        constexpr int ITER = (NPAIR + NT - 1) / NT;
-        constexpr int UB = 4;
+    // One row at a time; a thread takes point pairs x = 2 (tid + k NT) (128-bit loads), all of a row's
+    // loads are issued before any of them is consumed.
 #pragma unroll 1
-        for (int it0 = 0; it0 < ITER; it0 += UB) {
-            float4 a[UB], b[UB];
-            float2 w[UB], kx[UB];
-            float ky[UB];
+    for (int slot = 0; slot < NROWS; ++slot) {
+        const uint32_t jp = blockIdx.x * PAIRS + (slot >> 1);            // pair index, 0 = the self-paired rows 0, N/2
+        const uint32_t r = jp == 0 ? ((slot & 1) ? N / 2 : 0) : ((slot & 1) ? N - jp : jp);
+        constexpr int ITER = (N / 2 + NT - 1) / NT;
+        const float4* __restrict__ pf = reinterpret_cast<const float4*>(h0 + size_t(r) * N) + tid;             // propagate.comp:43
+        const float4* __restrict__ pr = reinterpret_cast<const float4*>(h0 + size_t(N - 1 - r) * N + N) - 1 - tid;   // :48
+        const float2* __restrict__ pw = reinterpret_cast<const float2*>(omega + size_t(r) * N) + tid;
+        const float2* __restrict__ pk = reinterpret_cast<const float2*>(kx_g) + tid;
+        // kx_g[g] = pi32 * float(uint(2g - N - 1)) / L, tabulated on the host with the shader's fp32 ops
+        const float ky = __ldg(kx_g + r);
+        float4 a[ITER], b[ITER];
+        float2 w[ITER], kx[ITER];
 #pragma unroll
-            for (int u = 0; u < UB; ++u) {
-                const int i = tid + (it0 + u) * NT;
-                const bool valid = (it0 + u < ITER) && i < NPAIR;
-                const int slot = valid ? i / (N / 2) : 0;
-                const uint32_t x = valid ? 2 * (i % (N / 2)) : 0;
-                const uint32_t jp = blockIdx.x * PAIRS + (slot >> 1);    // pair index, 0 = the self-paired rows 0, N/2
-                const uint32_t r = jp == 0 ? ((slot & 1) ? N / 2 : 0) : ((slot & 1) ? N - jp : jp);
-                const uint32_t index = x + N * r;                        // propagate.comp:43
-                const uint32_t index_neg = (N - r - 1u) * N + N - x - 2u;   // :48 for x+1; the partner of x is one further
-                a[u] = __ldg(reinterpret_cast<const float4*>(h0 + index));
-                b[u] = __ldg(reinterpret_cast<const float4*>(h0 + index_neg));
-                w[u] = __ldg(reinterpret_cast<const float2*>(omega + index));
-                // kx_g[g] = pi32 * float(uint(2g - N - 1)) / L, tabulated on the host with the shader's fp32 ops
-                kx[u] = __ldg(reinterpret_cast<const float2*>(kx_g + x));
-                ky[u] = __ldg(kx_g + r);
+        for (int u = 0; u < ITER; ++u) {
+            if (tid + u * NT < N / 2) {
+                a[u] = __ldg(pf + u * NT);
+                b[u] = __ldg(pr - u * NT);          // .zw is the partner of x, .xy the partner of x + 1
+                w[u] = __ldg(pw + u * NT);
+                kx[u] = __ldg(pk + u * NT);
             }
+        }
+        float4* row = S + slot * SP;
 #pragma unroll
-            for (int u = 0; u < UB; ++u) {
-                const int i = tid + (it0 + u) * NT;
-                if ((it0 + u < ITER) && i < NPAIR) {
-                    const int slot = i / (N / 2);
-                    const uint32_t x = 2 * (i % (N / 2));
-                    const float2 h_0 = propagate_point_fast(make_float2(a[u].x, a[u].y), make_float2(b[u].z, b[u].w), w[u].x, time);
-                    const float2 h_1 = propagate_point_fast(make_float2(a[u].z, a[u].w), make_float2(b[u].x, b[u].y), w[u].y, time);
-                    const float2 k_0 = unit_wave_vector_fast(kx[u].x, ky[u]);
-                    const float2 k_1 = unit_wave_vector_fast(kx[u].y, ky[u]);
-                    float4* row = S + slot * SP;
-                    row[x] = make_float4(h_0.x, h_0.y, k_0.x, k_0.y);
-                    row[x + 1] = make_float4(h_1.x, h_1.y, k_1.x, k_1.y);
-                    if (x == 0) row[N] = make_float4(h_0.x, h_0.y, k_0.x, k_0.y);
-                }
+        for (int u = 0; u < ITER; ++u) {
+            if (tid + u * NT < N / 2) {
+                const int x = 2 * (tid + u * NT);
+                const float2 h_0 = propagate_point_fast(make_float2(a[u].x, a[u].y), make_float2(b[u].z, b[u].w), w[u].x, time);
+                const float2 h_1 = propagate_point_fast(make_float2(a[u].z, a[u].w), make_float2(b[u].x, b[u].y), w[u].y, time);
+                const float2 k_0 = unit_wave_vector_fast(kx[u].x, ky);
+                const float2 k_1 = unit_wave_vector_fast(kx[u].y, ky);
+                row[x] = make_float4(h_0.x, h_0.y, k_0.x, k_0.y);
+                row[x + 1] = make_float4(h_1.x, h_1.y, k_1.x, k_1.y);
+                if (x == 0) row[N] = make_float4(h_0.x, h_0.y, k_0.x, k_0.y);
             }
         }
     }
@@ -187,11 +200,13 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
     }
     __syncwarp();
 
+    // destination row in the strip-major intermediate (row_off) and whether columns are mirrored
     float2* dst;
     bool mirrored = false;
-    if (seq == 0) dst = gp + size_t(j) * N;
-    else if (seq == 1) { dst = gp + size_t(self_paired ? N / 2 : N - j) * N; mirrored = !self_paired; }
-    else dst = gh + size_t(j) * N;
+    if (seq == 0) dst = gp + IL::row_off(j);
+    else if (seq == 1) { dst = gp + IL::row_off(self_paired ? N / 2 : N - j); mirrored = !self_paired; }
+    else dst = gh + IL::row_off(j);
+    const size_t strip_stride = seq == 2 ? IL::H_STRIP : IL::P_STRIP;
 #pragma unroll
     for (int i = 0; i < Cfg::SUB2; ++i) {
         const int n1 = k2 + R2 * i;
@@ -202,107 +217,245 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
 #pragma unroll
         for (int n2 = 0; n2 < R2; ++n2) {
             const uint32_t n = n1 + R1 * n2;
-            dst[mirrored ? ((N - n) & (N - 1)) : n] = u[n2];
+            const uint32_t col = mirrored ? ((N - n) & (N - 1)) : n;
+            dst[size_t(col / C) * strip_stride + col % C] = u[n2];
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// k_cols
+// k_cols: persistent, bulk-copy fed, warp-specialised
 // ------------------------------------------------------------------------------------------
-template <int N, int P, int C>
-__global__ void __launch_bounds__(3 * C * (N / P) / 2, 2)
-k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, const float2* __restrict__ tw_g,
-       float4* __restrict__ out_all, uint32_t first_tile)
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
-    using Cfg = LineCfg<N, P>;
-    constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2, LINE = Cfg::LINE;
-    constexpr int NTP = C * T;            // threads on the packed (dx, dz) columns
-    constexpr int HC = C / 2;             // packed height columns
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra WAIT_DONE;\n"
+        " bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+}  // namespace ptx
+
+template <int N, int P, int C>
+struct ColsCfg {
+    using Line = LineCfg<N, P>;
+    using IL = Inter<N, C, Line::R2>;
+    static constexpr int T = Line::T;
+    static constexpr int HC = C / 2;                  // packed height columns per strip
+    static constexpr int NTP = C * T;                 // threads on the packed (dx, dz) columns
+    static constexpr int NTH = HC * T;                // threads on the packed height columns
+    static constexpr int NTHREADS = NTP + NTH + 32;   // + one producer warp
+    static constexpr uint32_t P_BYTES = IL::P_STRIP * sizeof(float2);
+    static constexpr uint32_t H_BYTES = IL::H_STRIP * sizeof(float2);
+    static constexpr uint32_t XH_BYTES = HC * Line::LINE * sizeof(float2);
+    static_assert(sizeof(float) * N * C <= XH_BYTES, "height results must fit in XH");
+    static_assert(P_BYTES % 16 == 0 && H_BYTES % 16 == 0 && XH_BYTES % 16 == 0, "bulk copies need 16-byte granules");
+    static constexpr size_t SMEM = 2 * size_t(P_BYTES) + H_BYTES + XH_BYTES + 8 * sizeof(uint64_t);
+};
+
+// Work item = one strip of C columns of one tile. Per item:
+//   producer warp : bulk-copies the strip of GH (1 copy) and of GP (1 copy) into shared memory
+//   height warps  : build Z(y) = G(nA, y) + i G(nB, y) over the full column from the half-stored GH
+//                   (G(n, N-y) = conj G(n, y)), transform, park the two real results per packed column in HR
+//   packed warps  : transform the GP strip in place in shared memory, then write
+//                   out(x, y) = (dx, height, dz, 0) * sign / 2  (correction.comp:29-34)
+// GP is double-buffered so the next strip's copy overlaps this strip's transforms and stores.
+template <int N, int P, int C>
+__global__ void __launch_bounds__(ColsCfg<N, P, C>::NTHREADS, 1)
+k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, const float2* __restrict__ tw_g,
+       float4* __restrict__ out_all, uint32_t first_tile, uint32_t n_items)
+{
+    using CC = ColsCfg<N, P, C>;
+    using Cfg = typename CC::Line;
+    using IL = typename CC::IL;
+    constexpr int R1 = Cfg::R1, R2 = Cfg::R2, LINE = Cfg::LINE;
+    constexpr int NTP = CC::NTP, NTH = CC::NTH, HC = CC::HC;
+    constexpr int STRIPS = N / C;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* XP = reinterpret_cast<float2*>(smem_raw);      // [C][LINE]
-    float2* XH = XP + C * LINE;                            // [C/2][LINE]
-    float* HR = reinterpret_cast<float*>(XH);              // [N][C] height results, reuses XH once it is consumed
-    static_assert(sizeof(float) * N * C <= sizeof(float2) * HC * LINE, "height results must fit in XH");
-
-    const float2* __restrict__ gp = gp_all + size_t(blockIdx.y) * N * N;
-    const float2* __restrict__ gh = gh_all + size_t(blockIdx.y) * (N / 2) * N;
-    float4* __restrict__ out = out_all + size_t(first_tile + blockIdx.y) * N * N;
+    float2* PB0 = reinterpret_cast<float2*>(smem_raw);
+    float2* PB1 = reinterpret_cast<float2*>(smem_raw + CC::P_BYTES);
+    float2* GB = reinterpret_cast<float2*>(smem_raw + 2 * CC::P_BYTES);
+    float2* XH = reinterpret_cast<float2*>(smem_raw + 2 * CC::P_BYTES + CC::H_BYTES);
+    float* HR = reinterpret_cast<float*>(XH);          // [N][C] height results, reuses XH once it is drained
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * CC::P_BYTES + CC::H_BYTES + CC::XH_BYTES);
+    uint64_t* fullP = bars;        // [2] GP strip landed            (tx bytes)
+    uint64_t* emptyP = bars + 2;   // [2] packed warps drained PB    (NTP/32 arrivals)
+    uint64_t* fullG = bars + 4;    //     GH strip landed            (tx bytes)
+    uint64_t* emptyG = bars + 5;   //     height warps drained GB    (NTH/32 arrivals)
+    uint64_t* hrReady = bars + 6;  //     HR written                 (NTH/32 arrivals)
+    uint64_t* hrFree = bars + 7;   //     packed warps done with HR  (NTP/32 arrivals)
 
     const int tid = threadIdx.x;
-    const uint32_t n0 = blockIdx.x * C;
-
-    const bool is_p = tid < NTP;
-    // lanes run over columns first so that a warp's loads cover whole 32/64-byte row segments
-    const int c = is_p ? tid % C : (tid - NTP) % HC;
-    const int k2 = is_p ? tid / C : (tid - NTP) / HC;
-    float2* line = is_p ? XP + c * LINE : XH + c * LINE;
-
-    float2 v[R1];
-    if (is_p) {
-#pragma unroll
-        for (int k1 = 0; k1 < R1; ++k1) v[k1] = __ldg(gp + size_t(k1 * R2 + k2) * N + n0 + c);
-    } else {
-        // Z(y) = G(nA, y) + i G(nB, y) over the full column, G(n, N-y) = conj G(n, y),
-        // G(n, 0) = Re GH[0][n], G(n, N/2) = Im GH[0][n]
-        const uint32_t nA = n0 + c, nB = nA + HC;
-#pragma unroll
-        for (int k1 = 0; k1 < R1; ++k1) {
-            const uint32_t y = k1 * R2 + k2;
-            const uint32_t yy = (y == N / 2) ? 0u : (y > N / 2 ? N - y : y);
-            const float2 a = __ldg(gh + size_t(yy) * N + nA), b = __ldg(gh + size_t(yy) * N + nB);
-            float2 z;
-            if (y == 0) z = make_float2(a.x, b.x);
-            else if (y == N / 2) z = make_float2(a.y, b.y);
-            else if (y < N / 2) z = make_float2(a.x - b.y, a.y + b.x);
-            else z = make_float2(a.x + b.y, b.x - a.y);
-            v[k1] = z;
-        }
-    }
-    RegFft<R1>::run(v);
-#pragma unroll
-    for (int n1 = 0; n1 < R1; ++n1) {
-        const float2 y = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * R2 + k2));
-        line[Cfg::pad(n1 * R2 + k2)] = y;
+    const int lane = tid & 31;
+    if (tid == 0) {
+        ptx::mbar_init(fullP + 0, 1);
+        ptx::mbar_init(fullP + 1, 1);
+        ptx::mbar_init(emptyP + 0, NTP / 32);
+        ptx::mbar_init(emptyP + 1, NTP / 32);
+        ptx::mbar_init(fullG, 1);
+        ptx::mbar_init(emptyG, NTH / 32);
+        ptx::mbar_init(hrReady, NTH / 32);
+        ptx::mbar_init(hrFree, NTP / 32);
+        ptx::fence_mbar_init();
     }
     __syncthreads();
 
-    // pass 2 (+ output). Thread (c, g) owns outputs m = n1 + R1 n2, n1 = g + R2 i.
-    float2 u[Cfg::SUB2][R2];
-#pragma unroll
-    for (int i = 0; i < Cfg::SUB2; ++i) {
-        const int n1 = k2 + R2 * i;
-#pragma unroll
-        for (int k = 0; k < R2; ++k) u[i][k] = line[Cfg::pad(n1 * R2 + k)];
-    }
-    // the height threads have drained XH; only they need to agree before HR overwrites it
-    if (!is_p) asm volatile("bar.sync 1, %0;" ::"n"(HC * T) : "memory");
-#pragma unroll
-    for (int i = 0; i < Cfg::SUB2; ++i) {
-        const int n1 = k2 + R2 * i;
-        RegFft<R2>::run(u[i]);
-        if (!is_p) {                      // height columns: park the two real results for the packers
-#pragma unroll
-            for (int n2 = 0; n2 < R2; ++n2) {
-                const int m = n1 + R1 * n2;
-                HR[m * C + c] = u[i][n2].x;
-                HR[m * C + c + HC] = u[i][n2].y;
+    if (tid >= NTP + NTH) {
+        // ================= producer warp =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const uint32_t tl = item / STRIPS, strip = item % STRIPS;
+                const float2* srcH = gh_all + size_t(tl) * IL::H_TILE + size_t(strip) * IL::H_STRIP;
+                const float2* srcP = gp_all + size_t(tl) * IL::P_TILE + size_t(strip) * IL::P_STRIP;
+                if (it >= 1) ptx::mbar_wait(emptyG, (it - 1) & 1);
+                ptx::mbar_arrive_expect_tx(fullG, CC::H_BYTES);
+                ptx::bulk_g2s(GB, srcH, CC::H_BYTES, fullG);
+                const uint32_t b = it & 1;
+                if (it >= 2) ptx::mbar_wait(emptyP + b, ((it >> 1) - 1) & 1);
+                ptx::mbar_arrive_expect_tx(fullP + b, CC::P_BYTES);
+                ptx::bulk_g2s(b ? PB1 : PB0, srcP, CC::P_BYTES, fullP + b);
             }
         }
-    }
-    __syncthreads();                      // HR complete
-    if (is_p) {
+    } else if (tid >= NTP) {
+        // ================= height warps =================
+        const int ht = tid - NTP;
+        const int pc = ht % HC;               // packed column: real columns 2 pc and 2 pc + 1 of the strip
+        const int k2 = ht / HC;
+        float2* line = XH + pc * LINE;
+        uint32_t it = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            ptx::mbar_wait(fullG, it & 1);
+            float2 v[R1];
+            const float4* G4 = reinterpret_cast<const float4*>(GB) + pc;   // (G(nA, .), G(nB, .)) adjacent: one 128-bit load
+            constexpr int ROW4 = C / 2, GP4 = IL::GROUP_PITCH / 2;          // row / group pitch in float4
 #pragma unroll
-        for (int i = 0; i < Cfg::SUB2; ++i) {
-            const int n1 = k2 + R2 * i;
-#pragma unroll
-            for (int n2 = 0; n2 < R2; ++n2) {
-                const uint32_t m = n1 + R1 * n2;
-                // correction.comp:29 sign, times the 1/2 of the Hermitian fold
-                const float s = ((n0 + c + m) & 1u) ? 0.5f : -0.5f;
-                out[size_t(m) * N + n0 + c] = make_float4(u[i][n2].x * s, HR[m * C + c] * s, u[i][n2].y * s, 0.0f);
+            for (int k1 = 0; k1 < R1; ++k1) {
+                // y = k1 R2 + k2; rows y < N/2 are stored, y > N/2 mirror N - y, rows 0 and N/2 share stored row 0
+                float4 g;
+                if (k1 < R1 / 2) {
+                    g = G4[k1 * GP4 + k2 * ROW4];
+                    v[k1] = (k1 == 0 && k2 == 0) ? make_float2(g.x, g.z) : make_float2(g.x - g.w, g.y + g.z);
+                } else {
+                    // N - y = (R1 - k1 - 1) R2 + (R2 - k2) for k2 > 0, (R1 - k1) R2 for k2 = 0
+                    const int grp = k2 ? R1 - k1 - 1 : (R1 - k1) % R1, row = k2 ? R2 - k2 : 0;
+                    if (k1 == R1 / 2) {
+                        g = G4[(k2 ? grp : 0) * GP4 + row * ROW4];
+                        v[k1] = k2 ? make_float2(g.x + g.w, g.z - g.y) : make_float2(g.y, g.w);
+                    } else {
+                        g = G4[grp * GP4 + row * ROW4];
+                        v[k1] = make_float2(g.x + g.w, g.z - g.y);
+                    }
+                }
             }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(emptyG);
+            RegFft<R1>::run(v);
+#pragma unroll
+            for (int n1 = 1; n1 < R1; ++n1) v[n1] = cmul_tw(v[n1], __ldg(tw_g + n1 * R2 + k2));
+            if (it >= 1) ptx::mbar_wait(hrFree, (it - 1) & 1);     // the previous item's HR has been consumed
+#pragma unroll
+            for (int n1 = 0; n1 < R1; ++n1) line[Cfg::pad(n1 * R2 + k2)] = v[n1];
+            ptx::named_bar_sync<2, NTH>();
+            float2 u[Cfg::SUB2][R2];
+#pragma unroll
+            for (int i = 0; i < Cfg::SUB2; ++i) {
+                const int n1 = k2 + R2 * i;
+#pragma unroll
+                for (int k = 0; k < R2; ++k) u[i][k] = line[Cfg::pad(n1 * R2 + k)];
+            }
+            ptx::named_bar_sync<2, NTH>();                          // XH drained: HR may overwrite it
+#pragma unroll
+            for (int i = 0; i < Cfg::SUB2; ++i) {
+                const int n1 = k2 + R2 * i;
+                RegFft<R2>::run(u[i]);
+#pragma unroll
+                for (int n2 = 0; n2 < R2; ++n2) {
+                    const int m = n1 + R1 * n2;
+                    *reinterpret_cast<float2*>(HR + m * C + 2 * pc) = make_float2(u[i][n2].x, u[i][n2].y);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(hrReady);
+        }
+    } else {
+        // ================= packed (dx, dz) warps =================
+        const int c = tid % C;                // lanes run over columns first: a warp touches whole 64-byte rows
+        const int k2 = tid / C;
+        uint32_t it = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t tl = item / STRIPS, n0 = (item % STRIPS) * C;
+            const uint32_t b = it & 1;
+            float2* PB = b ? PB1 : PB0;
+            ptx::mbar_wait(fullP + b, (it >> 1) & 1);
+            float2 v[R1];
+            float2* col = PB + k2 * C + c;
+#pragma unroll
+            for (int k1 = 0; k1 < R1; ++k1) v[k1] = col[k1 * IL::GROUP_PITCH];
+            RegFft<R1>::run(v);
+#pragma unroll
+            for (int n1 = 0; n1 < R1; ++n1)
+                col[n1 * IL::GROUP_PITCH] = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * R2 + k2));
+            ptx::named_bar_sync<1, NTP>();
+            float2 u[Cfg::SUB2][R2];
+#pragma unroll
+            for (int i = 0; i < Cfg::SUB2; ++i) {
+                const int n1 = k2 + R2 * i;
+#pragma unroll
+                for (int k = 0; k < R2; ++k) u[i][k] = PB[n1 * IL::GROUP_PITCH + k * C + c];
+            }
+            ptx::fence_proxy_async();          // our generic-proxy writes to PB precede the next bulk copy into it
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(emptyP + b);
+#pragma unroll
+            for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2>::run(u[i]);
+            ptx::mbar_wait(hrReady, it & 1);
+            float4* __restrict__ out = out_all + size_t(first_tile + tl) * N * N + n0 + c;
+#pragma unroll
+            for (int i = 0; i < Cfg::SUB2; ++i) {
+                const int n1 = k2 + R2 * i;
+#pragma unroll
+                for (int n2 = 0; n2 < R2; ++n2) {
+                    const uint32_t m = n1 + R1 * n2;
+                    // correction.comp:29 sign, times the 1/2 of the Hermitian fold
+                    const float sg = ((n0 + c + m) & 1u) ? 0.5f : -0.5f;
+                    out[size_t(m) * N] = make_float4(u[i][n2].x * sg, HR[m * C + c] * sg, u[i][n2].y * sg, 0.0f);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(hrFree);
         }
     }
 }
@@ -313,36 +466,49 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
 struct FusedPlan {
     uint32_t n = 0, n_tiles = 0;
     float domain_size = 0.f;
+    int num_sms = 0;
+    int cols_blocks_per_sm = 1;  // persistent k_cols blocks resident per SM
     float2* d_tw = nullptr;      // [R1][R2] inter-pass twiddles
     float* d_kx = nullptr;       // [N] wave numbers, propagate.comp:45-46,50-53
-    float2* d_gp = nullptr;      // [tiles][N][N]
-    float2* d_gh = nullptr;      // [tiles][N/2][N]
+    float2* d_gp = nullptr;      // [tiles] strip-major packed (dx, dz) row-pass output
+    float2* d_gh = nullptr;      // [tiles] strip-major height row-pass output (N/2 rows)
 };
 
 template <int N, int P, int PAIRS, int C, int MINB>
 struct Launch {
     using Cfg = LineCfg<N, P>;
+    using CC = ColsCfg<N, P, C>;
+    using IL = typename CC::IL;
     static constexpr size_t smem_rows = sizeof(float4) * 2 * PAIRS * (N + 1);
-    static constexpr size_t smem_cols = sizeof(float2) * (C + C / 2) * Cfg::LINE;
 
-    static cudaError_t prepare()
+    static cudaError_t prepare(FusedPlan* p)
     {
-        cudaError_t e = cudaFuncSetAttribute(k_rows<N, P, PAIRS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_rows));
+        cudaError_t e = cudaFuncSetAttribute(k_rows<N, P, PAIRS, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_rows));
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(k_cols<N, P, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cols));
+        e = cudaFuncSetAttribute(k_cols<N, P, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(CC::SMEM));
+        if (e != cudaSuccess) return e;
+        int per_sm = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cols<N, P, C>, CC::NTHREADS, CC::SMEM);
+        p->cols_blocks_per_sm = per_sm < 1 ? 1 : per_sm;
+        return e;
     }
+    static size_t gp_floats2_per_tile() { return IL::P_TILE; }
+    static size_t gh_floats2_per_tile() { return IL::H_TILE; }
 
     static cudaError_t run(FusedPlan* p, const float2* h0, const float* omega, float4* out, float time,
                            uint32_t first_tile, uint32_t count, cudaStream_t s, cudaEvent_t* ev)
     {
         if (ev) cudaEventRecord(ev[0], s);
-        const dim3 grid_rows(N / 2 / PAIRS, count), grid_cols(N / C, count);
-        k_rows<N, P, PAIRS, MINB><<<grid_rows, 3 * PAIRS * Cfg::T, smem_rows, s>>>(h0, omega, p->d_tw, p->d_kx, p->d_gp, p->d_gh,
-                                                                             time, first_tile);
+        const dim3 grid_rows(N / 2 / PAIRS, count);
+        k_rows<N, P, PAIRS, C, MINB><<<grid_rows, 3 * PAIRS * Cfg::T, smem_rows, s>>>(h0, omega, p->d_tw, p->d_kx, p->d_gp, p->d_gh,
+                                                                                      time, first_tile);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (ev) cudaEventRecord(ev[1], s);
-        k_cols<N, P, C><<<grid_cols, 3 * C * Cfg::T / 2, smem_cols, s>>>(p->d_gp, p->d_gh, p->d_tw, out, first_tile);
+        const uint32_t items = count * (N / C);
+        const uint32_t slots = uint32_t(p->num_sms * p->cols_blocks_per_sm);
+        const uint32_t grid_cols = items < slots ? items : slots;
+        k_cols<N, P, C><<<grid_cols, CC::NTHREADS, CC::SMEM, s>>>(p->d_gp, p->d_gh, p->d_tw, out, first_tile, items);
         e = cudaGetLastError();
         if (ev) cudaEventRecord(ev[2], s);
         return e;
@@ -364,7 +530,7 @@ static void line_factors(uint32_t n, uint32_t& r1, uint32_t& r2)
     }
 }
 
-cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, float domain_size, int /*device*/)
+cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, float domain_size, int device)
 {
     *out = nullptr;
     if (!fused_supports(n)) return cudaErrorInvalidValue;
@@ -375,6 +541,7 @@ cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, flo
     p->domain_size = domain_size;
     cudaError_t e;
     auto bail = [&](cudaError_t err) { fused_plan_destroy(p); return err; };
+    if ((e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail(e);
 
     uint32_t r1, r2;
     line_factors(n, r1, r2);
@@ -395,15 +562,18 @@ cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, flo
     }
     if ((e = cudaMalloc(&p->d_kx, n * sizeof(float))) != cudaSuccess) return bail(e);
     if ((e = cudaMemcpy(p->d_kx, kx.data(), n * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
-    const size_t np = size_t(n) * n;
-    if ((e = cudaMalloc(&p->d_gp, size_t(n_tiles) * np * sizeof(float2))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&p->d_gh, size_t(n_tiles) * (np / 2) * sizeof(float2))) != cudaSuccess) return bail(e);
+    size_t gp_t, gh_t;
     switch (n) {
-        case 256: e = L256::prepare(); break;
-        case 512: e = L512::prepare(); break;
-        default: e = L1024::prepare(); break;
+        case 256: gp_t = L256::gp_floats2_per_tile(); gh_t = L256::gh_floats2_per_tile(); e = L256::prepare(p); break;
+        case 512: gp_t = L512::gp_floats2_per_tile(); gh_t = L512::gh_floats2_per_tile(); e = L512::prepare(p); break;
+        default: gp_t = L1024::gp_floats2_per_tile(); gh_t = L1024::gh_floats2_per_tile(); e = L1024::prepare(p); break;
     }
     if (e != cudaSuccess) return bail(e);
+    // pad rows of the intermediate are never written by k_rows but are copied (and ignored) by k_cols: zero them once
+    if ((e = cudaMalloc(&p->d_gp, size_t(n_tiles) * gp_t * sizeof(float2))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&p->d_gh, size_t(n_tiles) * gh_t * sizeof(float2))) != cudaSuccess) return bail(e);
+    if ((e = cudaMemset(p->d_gp, 0, size_t(n_tiles) * gp_t * sizeof(float2))) != cudaSuccess) return bail(e);
+    if ((e = cudaMemset(p->d_gh, 0, size_t(n_tiles) * gh_t * sizeof(float2))) != cudaSuccess) return bail(e);
     *out = p;
     return cudaSuccess;
 }
