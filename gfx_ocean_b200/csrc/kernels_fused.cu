@@ -200,13 +200,17 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
     }
     __syncwarp();
 
-    // destination row in the strip-major intermediate (row_off) and whether columns are mirrored
+    // Destination row in the strip-major intermediate. Thread n1 owns columns n = n1 + R1 n2: strip n / C and
+    // in-strip column n % C advance by a constant per n2 (R1 is a multiple of C), also for the mirrored
+    // sequence, whose column (N - n) mod N runs backwards; only n = 0 maps to itself there.
+    static_assert(R1 % C == 0, "pass-1 radix must cover whole strips");
     float2* dst;
     bool mirrored = false;
     if (seq == 0) dst = gp + IL::row_off(j);
     else if (seq == 1) { dst = gp + IL::row_off(self_paired ? N / 2 : N - j); mirrored = !self_paired; }
     else dst = gh + IL::row_off(j);
-    const size_t strip_stride = seq == 2 ? IL::H_STRIP : IL::P_STRIP;
+    const long strip_stride = seq == 2 ? IL::H_STRIP : IL::P_STRIP;
+    const long step = (mirrored ? -long(R1 / C) : long(R1 / C)) * strip_stride;
 #pragma unroll
     for (int i = 0; i < Cfg::SUB2; ++i) {
         const int n1 = k2 + R2 * i;
@@ -214,11 +218,16 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
 #pragma unroll
         for (int k = 0; k < R2; ++k) u[k] = line[Cfg::pad(n1 * R2 + k)];
         RegFft<R2>::run(u);
+        const uint32_t col0 = mirrored ? ((N - n1) & (N - 1)) : n1;          // column of n2 = 0
+        float2* q = dst + long(col0 / C) * strip_stride + col0 % C;
+        if (mirrored && n1 == 0) {
+            q[0] = u[0];                                                       // n = 0 -> column 0
+            q += long(N / C) * strip_stride;                                   // n = R1 n2 -> column N - R1 n2
 #pragma unroll
-        for (int n2 = 0; n2 < R2; ++n2) {
-            const uint32_t n = n1 + R1 * n2;
-            const uint32_t col = mirrored ? ((N - n) & (N - 1)) : n;
-            dst[size_t(col / C) * strip_stride + col % C] = u[n2];
+            for (int n2 = 1; n2 < R2; ++n2) q[n2 * step] = u[n2];
+        } else {
+#pragma unroll
+            for (int n2 = 0; n2 < R2; ++n2) q[n2 * step] = u[n2];
         }
     }
 }

@@ -42,7 +42,8 @@ __device__ __forceinline__ float2 unit_wave_vector(float kx, float ky)
 __device__ __forceinline__ float2 unit_wave_vector_fast(float kx, float ky)
 {
     const float l2 = fmaf(kx, kx, ky * ky);
-    float r = rsqrtf(l2);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l2));    // |k|^2 is never denormal on these grids
     r = r * fmaf(-0.5f * l2, r * r, 1.5f);
     r = l2 > 1.0e-20f ? r : 0.f;
     return make_float2(kx * r, ky * r);
