@@ -43,6 +43,8 @@ struct LineCfg {
     // line stride (in float2): >= pad(N-1)+1 and == 2 (mod 16) so that 8 lines x 2 rows of
     // 64-bit accesses fall into 16 distinct bank pairs
     static constexpr int LINE = ((pad(N - 1) + 1 - 2 + 15) / 16) * 16 + 2;
+    // same for 4 lines x 4 rows per half-warp (the packed height columns of k_cols): == 4 (mod 16)
+    static constexpr int LINE_H = ((pad(N - 1) + 1 - 4 + 15) / 16) * 16 + 4;
 };
 
 // Layout of the row-pass output in HBM/L2 (ours to choose: nothing outside the two kernels sees it).
@@ -287,10 +289,11 @@ struct ColsCfg {
     static constexpr int NTHREADS = NTP + NTH + 32;   // + one producer warp
     static constexpr uint32_t P_BYTES = IL::P_STRIP * sizeof(float2);
     static constexpr uint32_t H_BYTES = IL::H_STRIP * sizeof(float2);
-    static constexpr uint32_t XH_BYTES = HC * Line::LINE * sizeof(float2);
-    static_assert(sizeof(float) * N * C <= XH_BYTES, "height results must fit in XH");
+    static constexpr uint32_t XH_BYTES = HC * Line::LINE_H * sizeof(float2);
+    static_assert(sizeof(float) * N * C <= P_BYTES, "height results must fit in a drained GP buffer");
     static_assert(P_BYTES % 16 == 0 && H_BYTES % 16 == 0 && XH_BYTES % 16 == 0, "bulk copies need 16-byte granules");
-    static constexpr size_t SMEM = 2 * size_t(P_BYTES) + H_BYTES + XH_BYTES + 8 * sizeof(uint64_t);
+    static constexpr uint32_t TW_BYTES = N * sizeof(float2);
+    static constexpr size_t SMEM = 2 * size_t(P_BYTES) + H_BYTES + XH_BYTES + TW_BYTES + 10 * sizeof(uint64_t);
 };
 
 // Work item = one strip of C columns of one tile. Per item:
@@ -299,7 +302,8 @@ struct ColsCfg {
 //                   (G(n, N-y) = conj G(n, y)), transform, park the two real results per packed column in HR
 //   packed warps  : transform the GP strip in place in shared memory, then write
 //                   out(x, y) = (dx, height, dz, 0) * sign / 2  (correction.comp:29-34)
-// GP is double-buffered so the next strip's copy overlaps this strip's transforms and stores.
+// GP is double-buffered so the next strip's copy overlaps this strip's transforms and stores; HR lives in
+// the GP buffer the packed warps have just drained into registers, so the two roles only meet once per item.
 template <int N, int P, int C>
 __global__ void __launch_bounds__(ColsCfg<N, P, C>::NTHREADS, 1)
 k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, const float2* __restrict__ tw_g,
@@ -308,7 +312,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
     using CC = ColsCfg<N, P, C>;
     using Cfg = typename CC::Line;
     using IL = typename CC::IL;
-    constexpr int R1 = Cfg::R1, R2 = Cfg::R2, LINE = Cfg::LINE;
+    constexpr int R1 = Cfg::R1, R2 = Cfg::R2, LINE = Cfg::LINE_H;
     constexpr int NTP = CC::NTP, NTH = CC::NTH, HC = CC::HC;
     constexpr int STRIPS = N / C;
 
@@ -317,26 +321,28 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
     float2* PB1 = reinterpret_cast<float2*>(smem_raw + CC::P_BYTES);
     float2* GB = reinterpret_cast<float2*>(smem_raw + 2 * CC::P_BYTES);
     float2* XH = reinterpret_cast<float2*>(smem_raw + 2 * CC::P_BYTES + CC::H_BYTES);
-    float* HR = reinterpret_cast<float*>(XH);          // [N][C] height results, reuses XH once it is drained
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * CC::P_BYTES + CC::H_BYTES + CC::XH_BYTES);
-    uint64_t* fullP = bars;        // [2] GP strip landed            (tx bytes)
-    uint64_t* emptyP = bars + 2;   // [2] packed warps drained PB    (NTP/32 arrivals)
-    uint64_t* fullG = bars + 4;    //     GH strip landed            (tx bytes)
-    uint64_t* emptyG = bars + 5;   //     height warps drained GB    (NTH/32 arrivals)
-    uint64_t* hrReady = bars + 6;  //     HR written                 (NTH/32 arrivals)
-    uint64_t* hrFree = bars + 7;   //     packed warps done with HR  (NTP/32 arrivals)
+    float2* TW = reinterpret_cast<float2*>(smem_raw + 2 * CC::P_BYTES + CC::H_BYTES + CC::XH_BYTES);   // [R1][R2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * CC::P_BYTES + CC::H_BYTES + CC::XH_BYTES + CC::TW_BYTES);
+    uint64_t* fullP = bars;        // [2] GP strip landed in PB[b]               (tx bytes)         producer -> packed
+    uint64_t* drainedP = bars + 2; // [2] packed warps hold PB[b] in registers   (NTP/32 arrivals)  packed -> height
+    uint64_t* hrFree = bars + 4;   // [2] packed warps done with HR in PB[b]     (NTP/32 arrivals)  packed -> producer
+    uint64_t* fullG = bars + 6;    //     GH strip landed                        (tx bytes)         producer -> height
+    uint64_t* emptyG = bars + 7;   //     height warps drained GB                (NTH/32 arrivals)  height -> producer
+    uint64_t* hrReady = bars + 8;  //     HR written into PB[b]                  (NTH/32 arrivals)  height -> packed
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    for (int i = tid; i < N; i += CC::NTHREADS) TW[i] = tw_g[i];
     if (tid == 0) {
         ptx::mbar_init(fullP + 0, 1);
         ptx::mbar_init(fullP + 1, 1);
-        ptx::mbar_init(emptyP + 0, NTP / 32);
-        ptx::mbar_init(emptyP + 1, NTP / 32);
+        ptx::mbar_init(drainedP + 0, NTP / 32);
+        ptx::mbar_init(drainedP + 1, NTP / 32);
+        ptx::mbar_init(hrFree + 0, NTP / 32);
+        ptx::mbar_init(hrFree + 1, NTP / 32);
         ptx::mbar_init(fullG, 1);
         ptx::mbar_init(emptyG, NTH / 32);
         ptx::mbar_init(hrReady, NTH / 32);
-        ptx::mbar_init(hrFree, NTP / 32);
         ptx::fence_mbar_init();
     }
     __syncthreads();
@@ -353,7 +359,10 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                 ptx::mbar_arrive_expect_tx(fullG, CC::H_BYTES);
                 ptx::bulk_g2s(GB, srcH, CC::H_BYTES, fullG);
                 const uint32_t b = it & 1;
-                if (it >= 2) ptx::mbar_wait(emptyP + b, ((it >> 1) - 1) & 1);
+                if (it >= 2) {
+                    ptx::mbar_wait(hrFree + b, ((it >> 1) - 1) & 1);   // item it-2 is completely done with PB[b]
+                    ptx::fence_proxy_async();
+                }
                 ptx::mbar_arrive_expect_tx(fullP + b, CC::P_BYTES);
                 ptx::bulk_g2s(b ? PB1 : PB0, srcP, CC::P_BYTES, fullP + b);
             }
@@ -393,8 +402,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
             if (lane == 0) ptx::mbar_arrive(emptyG);
             RegFft<R1>::run(v);
 #pragma unroll
-            for (int n1 = 1; n1 < R1; ++n1) v[n1] = cmul_tw(v[n1], __ldg(tw_g + n1 * R2 + k2));
-            if (it >= 1) ptx::mbar_wait(hrFree, (it - 1) & 1);     // the previous item's HR has been consumed
+            for (int n1 = 1; n1 < R1; ++n1) v[n1] = cmul_tw(v[n1], TW[n1 * R2 + k2]);
 #pragma unroll
             for (int n1 = 0; n1 < R1; ++n1) line[Cfg::pad(n1 * R2 + k2)] = v[n1];
             ptx::named_bar_sync<2, NTH>();
@@ -405,11 +413,15 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
 #pragma unroll
                 for (int k = 0; k < R2; ++k) u[i][k] = line[Cfg::pad(n1 * R2 + k)];
             }
-            ptx::named_bar_sync<2, NTH>();                          // XH drained: HR may overwrite it
+            ptx::named_bar_sync<2, NTH>();                          // XH drained: the next item may overwrite it
+#pragma unroll
+            for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2>::run(u[i]);
+            const uint32_t b = it & 1;
+            float* HR = reinterpret_cast<float*>(b ? PB1 : PB0);     // [N][C] height results
+            ptx::mbar_wait(drainedP + b, (it >> 1) & 1);             // the packed warps hold this item's PB in registers
 #pragma unroll
             for (int i = 0; i < Cfg::SUB2; ++i) {
                 const int n1 = k2 + R2 * i;
-                RegFft<R2>::run(u[i]);
 #pragma unroll
                 for (int n2 = 0; n2 < R2; ++n2) {
                     const int m = n1 + R1 * n2;
@@ -436,7 +448,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
             RegFft<R1>::run(v);
 #pragma unroll
             for (int n1 = 0; n1 < R1; ++n1)
-                col[n1 * IL::GROUP_PITCH] = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * R2 + k2));
+                col[n1 * IL::GROUP_PITCH] = n1 == 0 ? v[0] : cmul_tw(v[n1], TW[n1 * R2 + k2]);
             ptx::named_bar_sync<1, NTP>();
             float2 u[Cfg::SUB2][R2];
 #pragma unroll
@@ -445,11 +457,11 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
 #pragma unroll
                 for (int k = 0; k < R2; ++k) u[i][k] = PB[n1 * IL::GROUP_PITCH + k * C + c];
             }
-            ptx::fence_proxy_async();          // our generic-proxy writes to PB precede the next bulk copy into it
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(emptyP + b);
+            if (lane == 0) ptx::mbar_arrive(drainedP + b);
 #pragma unroll
             for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2>::run(u[i]);
+            const float* HR = reinterpret_cast<const float*>(PB);
             ptx::mbar_wait(hrReady, it & 1);
             float4* __restrict__ out = out_all + size_t(first_tile + tl) * N * N + n0 + c;
 #pragma unroll
@@ -460,11 +472,12 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                     const uint32_t m = n1 + R1 * n2;
                     // correction.comp:29 sign, times the 1/2 of the Hermitian fold
                     const float sg = ((n0 + c + m) & 1u) ? 0.5f : -0.5f;
-                    out[size_t(m) * N] = make_float4(u[i][n2].x * sg, HR[m * C + c] * sg, u[i][n2].y * sg, 0.0f);
+                    __stcs(out + size_t(m) * N, make_float4(u[i][n2].x * sg, HR[m * C + c] * sg, u[i][n2].y * sg, 0.0f));
                 }
             }
+            ptx::fence_proxy_async();          // generic-proxy accesses to PB[b] precede the next bulk copy into it
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(hrFree);
+            if (lane == 0) ptx::mbar_arrive(hrFree + b);
         }
     }
 }
