@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libocean_b200.so")
+# OCEAN_B200_LIB selects an alternative build of the same library (A/B experiments, scripts/ab_build.sh)
+LIB_PATH = os.environ.get("OCEAN_B200_LIB") or os.path.join(HERE, "libocean_b200.so")
 
 ABI_VERSION = 1
 OK, ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_IO, ERR_NOT_READY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6

@@ -539,7 +539,15 @@ struct Launch {
 
 using L256 = Launch<256, 16, 2, 8, 4>;
 using L512 = Launch<512, 32, 2, 8, 4>;
-using L1024 = Launch<1024, 32, 1, 8, 6>;
+// k_rows at N=1024: 5 blocks/SM (128 registers, no spills) measured faster than 6 blocks/SM at 96 registers
+// (68 vs 76 us per 8 tiles); overridable for A/B builds (scripts/ab_build.sh)
+#ifndef OCEAN_ROWS_PAIRS_1024
+#define OCEAN_ROWS_PAIRS_1024 1
+#endif
+#ifndef OCEAN_ROWS_MINB_1024
+#define OCEAN_ROWS_MINB_1024 5
+#endif
+using L1024 = Launch<1024, 32, OCEAN_ROWS_PAIRS_1024, 8, OCEAN_ROWS_MINB_1024>;
 
 bool fused_supports(uint32_t n) { return n == 256 || n == 512 || n == 1024; }
 
