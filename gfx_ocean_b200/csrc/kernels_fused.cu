@@ -29,16 +29,25 @@
 
 namespace ocean {
 
+// A length-N line transform is done in two or three passes, N = R1 * R2 (* R3); every thread owns P = R1
+// points in registers and T = N / P threads share a line:
+//   pass 1  radix R1 over the most significant input digit (stride T), twiddle w_N^(n1 t)
+//   pass 2  radix R2 (stride R3), twiddle w_T^(n2 k3)            [P / R2 sub-transforms per thread]
+//   pass 3  radix R3 (contiguous), only when T > P               [P / R3 sub-transforms per thread]
+// with one trip through shared memory between passes; outputs appear at n = n1 + R1 n2 + R1 R2 n3.
 template <int N_, int P_>
 struct LineCfg {
     static constexpr int N = N_;
-    static constexpr int P = P_;        // points per thread
-    static constexpr int T = N / P;     // threads per line transform
-    static constexpr int R1 = P;        // pass-1 radix (stride T)
-    static constexpr int R2 = T;        // pass-2 radix (contiguous)
-    static constexpr int SUB2 = P / R2; // pass-2 sub-transforms per thread
-    static_assert(R1 * R2 == N && R2 <= P && T <= 32 && 32 % T == 0, "unsupported 2-pass factorisation");
-    static constexpr int PADQ = R2 < 32 ? R2 : 32;
+    static constexpr int P = P_;                  // points per thread
+    static constexpr int T = N / P;               // threads per line transform
+    static constexpr int R1 = P;
+    static constexpr int R2 = T < P ? T : P;
+    static constexpr int R3 = T / R2;
+    static constexpr int SUB2 = P / R2;           // pass-2 sub-transforms per thread
+    static constexpr int SUB3 = P / R3;           // pass-3 sub-transforms per thread (R3 > 1)
+    static_assert(R1 * R2 * R3 == N && R3 <= P && (T <= 32 ? 32 % T == 0 : T % 32 == 0), "unsupported factorisation");
+    static constexpr int GS = R3 == 1 ? R2 : 32;  // row-group size of the intermediate layout (see Inter)
+    static constexpr int PADQ = T < 32 ? T : 32;
     __host__ __device__ static constexpr int pad(int p) { return p + p / PADQ; }
     // line stride (in float2): >= pad(N-1)+1 and == 2 (mod 16) so that 8 lines x 2 rows of
     // 64-bit accesses fall into 16 distinct bank pairs
@@ -47,11 +56,44 @@ struct LineCfg {
     static constexpr int LINE_H = ((pad(N - 1) + 1 - 4 + 15) / 16) * 16 + 4;
 };
 
+// Passes 2 (and 3) of a line held in shared memory at line[pad(p)], for the three-pass factorisation.
+// `t` is the thread's index in the line; `sync` separates the passes; out(n, value) receives natural-order
+// results. Generic (not the tuned two-pass path): used for N = 2048.
+template <class Cfg, class Sync, class Out>
+__device__ __forceinline__ void line_passes_23(float2* line, int t, const float2* __restrict__ tw2, Sync sync, Out out)
+{
+    constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2, R3 = Cfg::R3;
+    const int g = t / R3, k3 = t % R3;
+#pragma unroll
+    for (int i = 0; i < Cfg::SUB2; ++i) {
+        const int n1 = g + R2 * i;
+        float2 u[R2];
+#pragma unroll
+        for (int k = 0; k < R2; ++k) u[k] = line[Cfg::pad(n1 * T + k * R3 + k3)];
+        RegFft<R2>::run(u);
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2)
+            line[Cfg::pad(n1 * T + n2 * R3 + k3)] = n2 == 0 ? u[0] : cmul_tw(u[n2], tw2[n2 * R3 + k3]);
+    }
+    sync();
+#pragma unroll
+    for (int i = 0; i < Cfg::SUB3; ++i) {
+        const int q = t + T * i, n1 = q % R1, n2 = q / R1;
+        float2 w[R3];
+#pragma unroll
+        for (int k = 0; k < R3; ++k) w[k] = line[Cfg::pad(n1 * T + n2 * R3 + k)];
+        RegFft<R3>::run(w);
+#pragma unroll
+        for (int n3 = 0; n3 < R3; ++n3) out(n1 + R1 * n2 + R1 * R2 * n3, w[n3]);
+    }
+}
+
 // Layout of the row-pass output in HBM/L2 (ours to choose: nothing outside the two kernels sees it).
 // Strip-major: all rows of the C columns [s*C, (s+1)*C) are contiguous, so the column pass pulls its
-// whole working set with ONE bulk copy; inside a strip rows are grouped by GS = R2 with one pad row
-// per group, which is exactly the shared-memory image the in-place column transform wants
-// (group pitch = 64 (mod 128) bytes for C = 8: pass-2 reads of neighbouring groups hit disjoint banks).
+// whole working set with ONE bulk copy; inside a strip rows are grouped by GS (= R2 for two-pass lines,
+// 32 for three-pass lines) with one pad row per group, which is exactly the shared-memory image the
+// in-place column transform wants (group pitch = 64 (mod 128) bytes for C = 8, 32 (mod 128) for C = 4:
+// pass-2 reads of neighbouring groups hit disjoint banks).
 //   GP: N rows (packed dx/dz field)      GH: N/2 rows (height field, row 0 = rows 0 and N/2 packed)
 template <int N, int C, int GS>
 struct Inter {
@@ -99,7 +141,7 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
     const uint32_t tile = first_tile + blockIdx.y;
     const float2* __restrict__ h0 = h0_all + size_t(tile) * N * N;
     const float* __restrict__ omega = omega_all + size_t(tile) * N * N;
-    using IL = Inter<N, C, Cfg::R2>;
+    using IL = Inter<N, C, Cfg::GS>;
     float2* __restrict__ gp = gp_all + size_t(blockIdx.y) * IL::P_TILE;
     float2* __restrict__ gh = gh_all + size_t(blockIdx.y) * IL::H_TILE;
 
@@ -167,7 +209,7 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
         const float4* PA = (seq == 0) ? S0 : S1;
         const float4* PB = self_paired ? PA : (seq == 0 ? S1 : S0);
         // element k1: x = k1 R2 + k2; A at (mirror_a ? N - x : x), B at the other one
-        const int step = mirror_a ? -R2 : R2;
+        const int step = mirror_a ? -T : T;
         const float4* pa = PA + (mirror_a ? N - k2 : k2);
         const float4* pb = PB + (mirror_a ? k2 : N - k2);
 #pragma unroll
@@ -181,14 +223,14 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
         const float2* pb = reinterpret_cast<const float2*>(S1 + N - k2);
 #pragma unroll
         for (int k1 = 0; k1 < R1; ++k1) {
-            const float2 A = pa[2 * k1 * R2], B = pb[-2 * k1 * R2];
+            const float2 A = pa[2 * k1 * T], B = pb[-2 * k1 * T];
             v[k1] = make_float2(A.x + B.x, A.y - B.y);
         }
     } else {
         // h_S(x, 0) + i h_S(x, N/2): both row transforms are real, so they share one complex transform
 #pragma unroll
         for (int k1 = 0; k1 < R1; ++k1) {
-            const int x = k1 * R2 + k2;
+            const int x = k1 * T + k2;
             const float4 a0 = S0[x], b0 = S0[N - x], a1 = S1[x], b1 = S1[N - x];
             v[k1] = make_float2((a0.x + b0.x) - (a1.y - b1.y), (a0.y - b0.y) + (a1.x + b1.x));
         }
@@ -197,10 +239,10 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
     RegFft<R1>::run(v);
 #pragma unroll
     for (int n1 = 0; n1 < R1; ++n1) {
-        const float2 y = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * R2 + k2));
-        line[Cfg::pad(n1 * R2 + k2)] = y;
+        const float2 y = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * T + k2));
+        line[Cfg::pad(n1 * T + k2)] = y;
     }
-    __syncwarp();
+    if constexpr (T <= 32) __syncwarp(); else __syncthreads();
 
     // Destination row in the strip-major intermediate. Thread n1 owns columns n = n1 + R1 n2: strip n / C and
     // in-strip column n % C advance by a constant per n2 (R1 is a multiple of C), also for the mirrored
@@ -212,6 +254,13 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
     else if (seq == 1) { dst = gp + IL::row_off(self_paired ? N / 2 : N - j); mirrored = !self_paired; }
     else dst = gh + IL::row_off(j);
     const long strip_stride = seq == 2 ? IL::H_STRIP : IL::P_STRIP;
+    if constexpr (Cfg::R3 > 1) {
+        line_passes_23<Cfg>(line, k2, tw_g + N, [] { __syncthreads(); }, [&](int n, float2 val) {
+            const uint32_t col = mirrored ? ((N - n) & (N - 1)) : n;
+            dst[long(col / C) * strip_stride + col % C] = val;
+        });
+        return;
+    }
     const long step = (mirrored ? -long(R1 / C) : long(R1 / C)) * strip_stride;
 #pragma unroll
     for (int i = 0; i < Cfg::SUB2; ++i) {
@@ -281,7 +330,7 @@ __device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1
 template <int N, int P, int C>
 struct ColsCfg {
     using Line = LineCfg<N, P>;
-    using IL = Inter<N, C, Line::R2>;
+    using IL = Inter<N, C, Line::GS>;
     static constexpr int T = Line::T;
     static constexpr int HC = C / 2;                  // packed height columns per strip
     static constexpr int NTP = C * T;                 // threads on the packed (dx, dz) columns
@@ -292,7 +341,7 @@ struct ColsCfg {
     static constexpr uint32_t XH_BYTES = HC * Line::LINE_H * sizeof(float2);
     static_assert(sizeof(float) * N * C <= P_BYTES, "height results must fit in a drained GP buffer");
     static_assert(P_BYTES % 16 == 0 && H_BYTES % 16 == 0 && XH_BYTES % 16 == 0, "bulk copies need 16-byte granules");
-    static constexpr uint32_t TW_BYTES = N * sizeof(float2);
+    static constexpr uint32_t TW_BYTES = (N + Line::T) * sizeof(float2);   // pass-1 twiddles [R1][T] + pass-2 twiddles [R2][R3]
     static constexpr size_t SMEM = 2 * size_t(P_BYTES) + H_BYTES + XH_BYTES + TW_BYTES + 10 * sizeof(uint64_t);
 };
 
@@ -312,7 +361,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
     using CC = ColsCfg<N, P, C>;
     using Cfg = typename CC::Line;
     using IL = typename CC::IL;
-    constexpr int R1 = Cfg::R1, R2 = Cfg::R2, LINE = Cfg::LINE_H;
+    constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2, R3 = Cfg::R3, LINE = Cfg::LINE_H;
     constexpr int NTP = CC::NTP, NTH = CC::NTH, HC = CC::HC;
     constexpr int STRIPS = N / C;
 
@@ -332,7 +381,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    for (int i = tid; i < N; i += CC::NTHREADS) TW[i] = tw_g[i];
+    for (int i = tid; i < N + Cfg::T; i += CC::NTHREADS) TW[i] = tw_g[i];
     if (tid == 0) {
         ptx::mbar_init(fullP + 0, 1);
         ptx::mbar_init(fullP + 1, 1);
@@ -379,54 +428,79 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
             float2 v[R1];
             const float4* G4 = reinterpret_cast<const float4*>(GB) + pc;   // (G(nA, .), G(nB, .)) adjacent: one 128-bit load
             constexpr int ROW4 = C / 2, GP4 = IL::GROUP_PITCH / 2;          // row / group pitch in float4
+            if constexpr (R3 == 1) {
 #pragma unroll
-            for (int k1 = 0; k1 < R1; ++k1) {
-                // y = k1 R2 + k2; rows y < N/2 are stored, y > N/2 mirror N - y, rows 0 and N/2 share stored row 0
-                float4 g;
-                if (k1 < R1 / 2) {
-                    g = G4[k1 * GP4 + k2 * ROW4];
-                    v[k1] = (k1 == 0 && k2 == 0) ? make_float2(g.x, g.z) : make_float2(g.x - g.w, g.y + g.z);
-                } else {
-                    // N - y = (R1 - k1 - 1) R2 + (R2 - k2) for k2 > 0, (R1 - k1) R2 for k2 = 0
-                    const int grp = k2 ? R1 - k1 - 1 : (R1 - k1) % R1, row = k2 ? R2 - k2 : 0;
-                    if (k1 == R1 / 2) {
-                        g = G4[(k2 ? grp : 0) * GP4 + row * ROW4];
-                        v[k1] = k2 ? make_float2(g.x + g.w, g.z - g.y) : make_float2(g.y, g.w);
+                for (int k1 = 0; k1 < R1; ++k1) {
+                    // y = k1 R2 + k2; rows y < N/2 are stored, y > N/2 mirror N - y, rows 0 and N/2 share stored row 0
+                    float4 g;
+                    if (k1 < R1 / 2) {
+                        g = G4[k1 * GP4 + k2 * ROW4];
+                        v[k1] = (k1 == 0 && k2 == 0) ? make_float2(g.x, g.z) : make_float2(g.x - g.w, g.y + g.z);
                     } else {
-                        g = G4[grp * GP4 + row * ROW4];
-                        v[k1] = make_float2(g.x + g.w, g.z - g.y);
+                        // N - y = (R1 - k1 - 1) R2 + (R2 - k2) for k2 > 0, (R1 - k1) R2 for k2 = 0
+                        const int grp = k2 ? R1 - k1 - 1 : (R1 - k1) % R1, row = k2 ? R2 - k2 : 0;
+                        if (k1 == R1 / 2) {
+                            g = G4[(k2 ? grp : 0) * GP4 + row * ROW4];
+                            v[k1] = k2 ? make_float2(g.x + g.w, g.z - g.y) : make_float2(g.y, g.w);
+                        } else {
+                            g = G4[grp * GP4 + row * ROW4];
+                            v[k1] = make_float2(g.x + g.w, g.z - g.y);
+                        }
                     }
+                }
+            } else {
+#pragma unroll
+                for (int k1 = 0; k1 < R1; ++k1) {
+                    const uint32_t y = k1 * T + k2;                          // generic: any row grouping
+                    const uint32_t yy = (y == N / 2) ? 0u : (y > N / 2 ? N - y : y);
+                    const float4 g = G4[IL::row_off(yy) / 2];
+                    if (y == 0) v[k1] = make_float2(g.x, g.z);
+                    else if (y == N / 2) v[k1] = make_float2(g.y, g.w);
+                    else if (y < N / 2) v[k1] = make_float2(g.x - g.w, g.y + g.z);
+                    else v[k1] = make_float2(g.x + g.w, g.z - g.y);
                 }
             }
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(emptyG);
             RegFft<R1>::run(v);
 #pragma unroll
-            for (int n1 = 1; n1 < R1; ++n1) v[n1] = cmul_tw(v[n1], TW[n1 * R2 + k2]);
+            for (int n1 = 1; n1 < R1; ++n1) v[n1] = cmul_tw(v[n1], TW[n1 * T + k2]);
 #pragma unroll
-            for (int n1 = 0; n1 < R1; ++n1) line[Cfg::pad(n1 * R2 + k2)] = v[n1];
+            for (int n1 = 0; n1 < R1; ++n1) line[Cfg::pad(n1 * T + k2)] = v[n1];
             ptx::named_bar_sync<2, NTH>();
-            float2 u[Cfg::SUB2][R2];
-#pragma unroll
-            for (int i = 0; i < Cfg::SUB2; ++i) {
-                const int n1 = k2 + R2 * i;
-#pragma unroll
-                for (int k = 0; k < R2; ++k) u[i][k] = line[Cfg::pad(n1 * R2 + k)];
-            }
-            ptx::named_bar_sync<2, NTH>();                          // XH drained: the next item may overwrite it
-#pragma unroll
-            for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2>::run(u[i]);
             const uint32_t b = it & 1;
             float* HR = reinterpret_cast<float*>(b ? PB1 : PB0);     // [N][C] height results
-            ptx::mbar_wait(drainedP + b, (it >> 1) & 1);             // the packed warps hold this item's PB in registers
+            if constexpr (R3 == 1) {
+                float2 u[Cfg::SUB2][R2];
 #pragma unroll
-            for (int i = 0; i < Cfg::SUB2; ++i) {
-                const int n1 = k2 + R2 * i;
+                for (int i = 0; i < Cfg::SUB2; ++i) {
+                    const int n1 = k2 + R2 * i;
 #pragma unroll
-                for (int n2 = 0; n2 < R2; ++n2) {
-                    const int m = n1 + R1 * n2;
-                    *reinterpret_cast<float2*>(HR + m * C + 2 * pc) = make_float2(u[i][n2].x, u[i][n2].y);
+                    for (int k = 0; k < R2; ++k) u[i][k] = line[Cfg::pad(n1 * R2 + k)];
                 }
+                ptx::named_bar_sync<2, NTH>();                          // XH drained: the next item may overwrite it
+#pragma unroll
+                for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2>::run(u[i]);
+                ptx::mbar_wait(drainedP + b, (it >> 1) & 1);             // the packed warps hold this item's PB in registers
+#pragma unroll
+                for (int i = 0; i < Cfg::SUB2; ++i) {
+                    const int n1 = k2 + R2 * i;
+#pragma unroll
+                    for (int n2 = 0; n2 < R2; ++n2) {
+                        const int m = n1 + R1 * n2;
+                        *reinterpret_cast<float2*>(HR + m * C + 2 * pc) = make_float2(u[i][n2].x, u[i][n2].y);
+                    }
+                }
+            } else {
+                // pass 2 in XH, then wait for the packed warps before pass 3 streams its results into HR
+                bool waited = false;
+                line_passes_23<Cfg>(line, k2, TW + N, [&] {
+                    ptx::named_bar_sync<2, NTH>();
+                    ptx::mbar_wait(drainedP + b, (it >> 1) & 1);
+                    waited = true;
+                }, [&](int m, float2 val) { *reinterpret_cast<float2*>(HR + m * C + 2 * pc) = val; });
+                (void)waited;
+                ptx::named_bar_sync<2, NTH>();                          // XH drained: the next item may overwrite it
             }
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(hrReady);
@@ -442,37 +516,77 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
             float2* PB = b ? PB1 : PB0;
             ptx::mbar_wait(fullP + b, (it >> 1) & 1);
             float2 v[R1];
-            float2* col = PB + k2 * C + c;
+            // position p = k1 T + k2 lives at row_off(p) + c; T is a multiple of the group size, so k1 strides whole groups
+            float2* col = PB + IL::row_off(k2) + c;
+            constexpr int K1_STRIDE = (T / Cfg::GS) * IL::GROUP_PITCH;
 #pragma unroll
-            for (int k1 = 0; k1 < R1; ++k1) v[k1] = col[k1 * IL::GROUP_PITCH];
+            for (int k1 = 0; k1 < R1; ++k1) v[k1] = col[k1 * K1_STRIDE];
             RegFft<R1>::run(v);
 #pragma unroll
             for (int n1 = 0; n1 < R1; ++n1)
-                col[n1 * IL::GROUP_PITCH] = n1 == 0 ? v[0] : cmul_tw(v[n1], TW[n1 * R2 + k2]);
+                col[n1 * K1_STRIDE] = n1 == 0 ? v[0] : cmul_tw(v[n1], TW[n1 * T + k2]);
             ptx::named_bar_sync<1, NTP>();
-            float2 u[Cfg::SUB2][R2];
-#pragma unroll
-            for (int i = 0; i < Cfg::SUB2; ++i) {
-                const int n1 = k2 + R2 * i;
-#pragma unroll
-                for (int k = 0; k < R2; ++k) u[i][k] = PB[n1 * IL::GROUP_PITCH + k * C + c];
-            }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(drainedP + b);
-#pragma unroll
-            for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2>::run(u[i]);
-            const float* HR = reinterpret_cast<const float*>(PB);
-            ptx::mbar_wait(hrReady, it & 1);
             float4* __restrict__ out = out_all + size_t(first_tile + tl) * N * N + n0 + c;
+            const float* HR = reinterpret_cast<const float*>(PB);
+            if constexpr (R3 == 1) {
+                float2 u[Cfg::SUB2][R2];
 #pragma unroll
-            for (int i = 0; i < Cfg::SUB2; ++i) {
-                const int n1 = k2 + R2 * i;
+                for (int i = 0; i < Cfg::SUB2; ++i) {
+                    const int n1 = k2 + R2 * i;
 #pragma unroll
-                for (int n2 = 0; n2 < R2; ++n2) {
-                    const uint32_t m = n1 + R1 * n2;
-                    // correction.comp:29 sign, times the 1/2 of the Hermitian fold
-                    const float sg = ((n0 + c + m) & 1u) ? 0.5f : -0.5f;
-                    __stcs(out + size_t(m) * N, make_float4(u[i][n2].x * sg, HR[m * C + c] * sg, u[i][n2].y * sg, 0.0f));
+                    for (int k = 0; k < R2; ++k) u[i][k] = PB[n1 * IL::GROUP_PITCH + k * C + c];
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(drainedP + b);
+#pragma unroll
+                for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2>::run(u[i]);
+                ptx::mbar_wait(hrReady, it & 1);
+#pragma unroll
+                for (int i = 0; i < Cfg::SUB2; ++i) {
+                    const int n1 = k2 + R2 * i;
+#pragma unroll
+                    for (int n2 = 0; n2 < R2; ++n2) {
+                        const uint32_t m = n1 + R1 * n2;
+                        // correction.comp:29 sign, times the 1/2 of the Hermitian fold
+                        const float sg = ((n0 + c + m) & 1u) ? 0.5f : -0.5f;
+                        __stcs(out + size_t(m) * N, make_float4(u[i][n2].x * sg, HR[m * C + c] * sg, u[i][n2].y * sg, 0.0f));
+                    }
+                }
+            } else {
+                // pass 2 in place, pass 3 into registers, then the same exchange with the height warps
+                const int g = k2 / R3, k3 = k2 % R3;
+#pragma unroll
+                for (int i = 0; i < Cfg::SUB2; ++i) {
+                    const int n1 = g + R2 * i;
+                    float2 u[R2];
+#pragma unroll
+                    for (int k = 0; k < R2; ++k) u[k] = PB[IL::row_off(n1 * T + k * R3 + k3) + c];
+                    RegFft<R2>::run(u);
+#pragma unroll
+                    for (int n2 = 0; n2 < R2; ++n2)
+                        PB[IL::row_off(n1 * T + n2 * R3 + k3) + c] = n2 == 0 ? u[0] : cmul_tw(u[n2], TW[N + n2 * R3 + k3]);
+                }
+                ptx::named_bar_sync<1, NTP>();
+                float2 w[Cfg::SUB3][R3];
+#pragma unroll
+                for (int i = 0; i < Cfg::SUB3; ++i) {
+                    const int q = k2 + T * i, n1 = q % R1, n2 = q / R1;
+#pragma unroll
+                    for (int k = 0; k < R3; ++k) w[i][k] = PB[IL::row_off(n1 * T + n2 * R3 + k) + c];
+                    RegFft<R3>::run(w[i]);
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(drainedP + b);
+                ptx::mbar_wait(hrReady, it & 1);
+#pragma unroll
+                for (int i = 0; i < Cfg::SUB3; ++i) {
+                    const int q = k2 + T * i, n1 = q % R1, n2 = q / R1;
+#pragma unroll
+                    for (int n3 = 0; n3 < R3; ++n3) {
+                        const uint32_t m = n1 + R1 * n2 + R1 * R2 * n3;
+                        const float sg = ((n0 + c + m) & 1u) ? 0.5f : -0.5f;
+                        __stcs(out + size_t(m) * N, make_float4(w[i][n3].x * sg, HR[m * C + c] * sg, w[i][n3].y * sg, 0.0f));
+                    }
                 }
             }
             ptx::fence_proxy_async();          // generic-proxy accesses to PB[b] precede the next bulk copy into it
@@ -539,6 +653,7 @@ struct Launch {
 
 using L256 = Launch<256, 16, 2, 8, 4>;
 using L512 = Launch<512, 32, 2, 8, 4>;
+using L2048 = Launch<2048, 32, 1, 4, 2>;   // three-pass lines (32 x 32 x 2), strips of 4 columns
 // k_rows at N=1024: 5 blocks/SM (128 registers, no spills) measured faster than 6 blocks/SM at 96 registers
 // (68 vs 76 us per 8 tiles); overridable for A/B builds (scripts/ab_build.sh)
 #ifndef OCEAN_ROWS_PAIRS_1024
@@ -549,15 +664,24 @@ using L512 = Launch<512, 32, 2, 8, 4>;
 #endif
 using L1024 = Launch<1024, 32, OCEAN_ROWS_PAIRS_1024, 8, OCEAN_ROWS_MINB_1024>;
 
-bool fused_supports(uint32_t n) { return n == 256 || n == 512 || n == 1024; }
+bool fused_supports(uint32_t n) { return n == 256 || n == 512 || n == 1024 || n == 2048; }
 
-static void line_factors(uint32_t n, uint32_t& r1, uint32_t& r2)
+// pass-1 twiddles w_N^(n1 t) as [R1][T], then pass-2 twiddles w_T^(n2 k3) as [R2][R3]
+template <class Cfg>
+static std::vector<float2> make_twiddles()
 {
-    switch (n) {
-        case 256: r1 = 16; r2 = 16; break;
-        case 512: r1 = 32; r2 = 16; break;
-        default: r1 = 32; r2 = n / 32; break;
-    }
+    std::vector<float2> tw(Cfg::N + Cfg::T);
+    for (int n1 = 0; n1 < Cfg::R1; ++n1)
+        for (int t = 0; t < Cfg::T; ++t) {
+            const double th = 2.0 * kPiD * double((n1 * t) % Cfg::N) / double(Cfg::N);
+            tw[n1 * Cfg::T + t] = make_float2(float(std::cos(th)), float(std::sin(th)));
+        }
+    for (int n2 = 0; n2 < Cfg::R2; ++n2)
+        for (int k3 = 0; k3 < Cfg::R3; ++k3) {
+            const double th = 2.0 * kPiD * double((n2 * k3) % Cfg::T) / double(Cfg::T);
+            tw[Cfg::N + n2 * Cfg::R3 + k3] = make_float2(float(std::cos(th)), float(std::sin(th)));
+        }
+    return tw;
 }
 
 cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, float domain_size, int device)
@@ -573,16 +697,15 @@ cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, flo
     auto bail = [&](cudaError_t err) { fused_plan_destroy(p); return err; };
     if ((e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail(e);
 
-    uint32_t r1, r2;
-    line_factors(n, r1, r2);
-    std::vector<float2> tw(n);
-    for (uint32_t n1 = 0; n1 < r1; ++n1)
-        for (uint32_t k2 = 0; k2 < r2; ++k2) {
-            const double th = 2.0 * kPiD * double((n1 * k2) % n) / double(n);
-            tw[n1 * r2 + k2] = make_float2(float(std::cos(th)), float(std::sin(th)));
-        }
-    if ((e = cudaMalloc(&p->d_tw, n * sizeof(float2))) != cudaSuccess) return bail(e);
-    if ((e = cudaMemcpy(p->d_tw, tw.data(), n * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
+    std::vector<float2> tw;
+    switch (n) {
+        case 256: tw = make_twiddles<L256::Cfg>(); break;
+        case 512: tw = make_twiddles<L512::Cfg>(); break;
+        case 1024: tw = make_twiddles<L1024::Cfg>(); break;
+        default: tw = make_twiddles<L2048::Cfg>(); break;
+    }
+    if ((e = cudaMalloc(&p->d_tw, tw.size() * sizeof(float2))) != cudaSuccess) return bail(e);
+    if ((e = cudaMemcpy(p->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
     // the shader's fp32 arithmetic, op for op: k = pi * float(uint(2g - N - 1)) / domain_size
     std::vector<float> kx(n);
     for (uint32_t g = 0; g < n; ++g) {
@@ -596,7 +719,8 @@ cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, flo
     switch (n) {
         case 256: gp_t = L256::gp_floats2_per_tile(); gh_t = L256::gh_floats2_per_tile(); e = L256::prepare(p); break;
         case 512: gp_t = L512::gp_floats2_per_tile(); gh_t = L512::gh_floats2_per_tile(); e = L512::prepare(p); break;
-        default: gp_t = L1024::gp_floats2_per_tile(); gh_t = L1024::gh_floats2_per_tile(); e = L1024::prepare(p); break;
+        case 1024: gp_t = L1024::gp_floats2_per_tile(); gh_t = L1024::gh_floats2_per_tile(); e = L1024::prepare(p); break;
+        default: gp_t = L2048::gp_floats2_per_tile(); gh_t = L2048::gh_floats2_per_tile(); e = L2048::prepare(p); break;
     }
     if (e != cudaSuccess) return bail(e);
     // pad rows of the intermediate are never written by k_rows but are copied (and ignored) by k_cols: zero them once
@@ -626,6 +750,7 @@ cudaError_t fused_enqueue(FusedPlan* p, const float2* h0, const float* omega, fl
         case 256: e = L256::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
         case 512: e = L512::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
         case 1024: e = L1024::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
+        case 2048: e = L2048::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
         default: return cudaErrorInvalidValue;
     }
     if (launches) *launches = 2;

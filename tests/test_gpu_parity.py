@@ -86,10 +86,11 @@ def test_fused_and_literal_agree(shipped_fused, shipped_literal):
     assert max(max_rel_err(a, b)) <= 5e-6
 
 
-@pytest.mark.parametrize("n", [256, 1024])
+@pytest.mark.parametrize("n", [256, 1024, 2048])
 @pytest.mark.parametrize("t", [0.0, 1.0, 37.5])
 def test_synthetic_tiles_match_oracle(n, t, oracle):
-    """BASELINE.json configs 3: seeded synthetic grids at other resolutions."""
+    """BASELINE.json configs 3/4: seeded synthetic grids at other resolutions
+    (2048: three-pass lines, strips of 4 columns)."""
     h0, w = synthetic_tile(n, tile=3)
     with Ocean.new(n, 1000.0, w, h0) as o:
         o.update(t)
@@ -110,6 +111,19 @@ def test_golden_synth_1024(golden_synth):
             py, px = golden_synth["n1024_probe_y"], golden_synth["n1024_probe_x"]
             err = np.abs(out[py, px, :3] - golden_synth[f"n1024_probe_out_{i}"][:, :3]).max(axis=0) / golden_synth[f"n1024_max_abs_{i}"]
             assert err.max() <= TOL
+
+
+def test_golden_synth_2048_fused_and_literal(golden_synth):
+    """BASELINE.json config 4 (2048 x 2048): both pipelines against the committed golden probes."""
+    h0, w = synthetic_tile(2048, 0)
+    py, px = golden_synth["n2048_probe_y"], golden_synth["n2048_probe_x"]
+    for pipeline in (PIPELINE_FUSED, PIPELINE_LITERAL):
+        with Ocean.new(2048, 1000.0, w, h0, pipeline=pipeline) as o:
+            o.update(float(golden_synth["n2048_times"][0]))
+            out = o.read_back()
+        err = np.abs(out[py, px, :3] - golden_synth["n2048_probe_out_0"][:, :3]).max(axis=0) / golden_synth["n2048_max_abs_0"]
+        assert err.max() <= TOL
+        check_w_channel(out)
 
 
 def test_tiles_are_independent_and_bit_identical_to_single_tile_runs():
