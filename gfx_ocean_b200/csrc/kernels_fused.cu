@@ -326,6 +326,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+// Same, for the producer thread: back off between polls so the spin does not eat issue slots of the
+// compute warps sharing its scheduler (a buffer frees up once per item, microseconds apart).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
@@ -416,12 +431,12 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                 const uint32_t tl = item / STRIPS, strip = item % STRIPS;
                 const float2* srcH = gh_all + size_t(tl) * IL::H_TILE + size_t(strip) * IL::H_STRIP;
                 const float2* srcP = gp_all + size_t(tl) * IL::P_TILE + size_t(strip) * IL::P_STRIP;
-                if (it >= 1) ptx::mbar_wait(emptyG, (it - 1) & 1);
+                if (it >= 1) ptx::mbar_wait_backoff(emptyG, (it - 1) & 1);
                 ptx::mbar_arrive_expect_tx(fullG, CC::H_BYTES);
                 ptx::bulk_g2s(GB, srcH, CC::H_BYTES, fullG);
                 const uint32_t b = it & 1;
                 if (it >= 2) {
-                    ptx::mbar_wait(hrFree + b, ((it >> 1) - 1) & 1);   // item it-2 is completely done with PB[b]
+                    ptx::mbar_wait_backoff(hrFree + b, ((it >> 1) - 1) & 1);   // item it-2 is completely done with PB[b]
                     ptx::fence_proxy_async();
                 }
                 ptx::mbar_arrive_expect_tx(fullP + b, CC::P_BYTES);
