@@ -236,6 +236,26 @@ def main():
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     fps = world * len(my_tiles) * K / (ms * 1e-3)
 
+    # ---- latency mode: ONE tile per ocean_update, rotating over the context's tiles so each frame's inputs
+    #      are L2-cold (8 x 12 MB inputs + 8 x 16 MB outputs > 126 MB L2); this is BASELINE.json configs[2]
+    #      taken literally (a single 1024^2 ocean per frame)
+    single = None
+    if len(my_tiles) >= 8:
+        ks = max(200, K // 4)
+        with torch.cuda.stream(stream):
+            for i in range(W):
+                ocean.update_tiles(args.dt * i, i % len(my_tiles), 1)
+            barrier()
+            ev0.record(stream)
+            for i in range(ks):
+                ocean.update_tiles(args.dt * i, i % len(my_tiles), 1)
+            ev1.record(stream)
+            barrier()
+        ms1 = max_over_ranks(ev0.elapsed_time(ev1))
+        single = {"value": world * ks / (ms1 * 1e-3), "unit": UNIT, "us_per_frame": 1e3 * ms1 / ks, "steps": ks,
+                  "alg_GBps": ALG_BYTES_PER_POINT * n * n / (ms1 / ks * 1e-3) / 1e9,
+                  "note": "one tile per ocean_update (2 launches), rotating over the tiles so inputs are L2-cold"}
+
     # ---- per-kernel durations (CUDA events between the two launches, same stream)
     stage_ms = None
     if args.pipeline == "fused":
@@ -284,6 +304,7 @@ def main():
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": 12, "d2h_bytes_per_step": nbytes_out,
                     "steps": e2e_steps, "note": "Ocean.update(t) + read_back of every tile into pinned host memory + sync, per step"},
             "step_alg_GBps": alg_step / (ms / K * 1e-3) / 1e9,
+            "single_tile_per_update": single,
         }
         if stage_ms:
             alg = [ALG_BYTES_ROWS * n * n * len(my_tiles), ALG_BYTES_COLS * n * n * len(my_tiles)]
