@@ -128,25 +128,6 @@ __device__ __forceinline__ float2 rot_mul_conj(float4 s)
     return make_float2(fmaf(s.w, s.x, -s.z * s.y), -fmaf(s.w, s.y, s.z * s.x));
 }
 
-// Out-of-line general path of phase A for one thread's share of a row: any phase magnitude (libdevice sincos
-// beyond 1e5 rad). Re-reads its inputs; only taken when |omega * t| can exceed 1e5 (t of the order of hours).
-__device__ __noinline__ void propagate_row_general(const float2* __restrict__ h0, const float* __restrict__ omega,
-                                                   const float* __restrict__ kx_g, uint32_t r, uint32_t n, float time,
-                                                   int tid, int nt, float4* row)
-{
-    const float ky = __ldg(kx_g + r);
-    for (uint32_t pair = tid; pair < n / 2; pair += nt) {                // the same point pairs as the fast path
-        for (uint32_t x = 2 * pair; x < 2 * pair + 2; ++x) {
-            const uint32_t index = x + n * r;                            // propagate.comp:43
-            const uint32_t index_neg = (n - r - 1u) * n + n - x - 1u;    // :48
-            const float2 h = propagate_point_fast(__ldg(h0 + index), __ldg(h0 + index_neg), __ldg(omega + index), time);
-            const float2 kh = unit_wave_vector_fast(__ldg(kx_g + x), ky);
-            row[x] = make_float4(h.x, h.y, kh.x, kh.y);
-            if (x == 0) row[n] = make_float4(h.x, h.y, kh.x, kh.y);
-        }
-    }
-}
-
 template <int N, int P, int PAIRS, int C, int MINB>
 __global__ void __launch_bounds__(3 * PAIRS * (N / P), MINB)
 k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, const float2* __restrict__ tw_g,
@@ -175,53 +156,43 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
     pdl_launch_dependents();
 
     // ---- phase A: propagate.comp for the block's 2*PAIRS rows -> shared memory.
-    // One row at a time; a thread takes point pairs x = 2 (tid + u NT) (128-bit loads), all of a row's loads in
-    // flight before the first is consumed. The arithmetic of a row is ONE straight-line block (no per-point
-    // branches) so the 2 * ITER independent sincos / unit-vector chains interleave; the rare huge-phase case
-    // (|omega t| > 1e5, libdevice's Payne-Hanek path) is decided once per thread and row.
+    // One row at a time; a thread takes point pairs x = 2 (tid + k NT) (128-bit loads), all of a row's
+    // loads are issued before any of them is consumed.
 #pragma unroll 1
     for (int slot = 0; slot < NROWS; ++slot) {
         const uint32_t jp = blockIdx.x * PAIRS + (slot >> 1);            // pair index, 0 = the self-paired rows 0, N/2
         const uint32_t r = jp == 0 ? ((slot & 1) ? N / 2 : 0) : ((slot & 1) ? N - jp : jp);
         constexpr int ITER = (N / 2 + NT - 1) / NT;
-        constexpr bool TAIL = (N / 2) % NT != 0;     // the last step is only taken by the first (N/2) % NT threads
         const float4* __restrict__ pf = reinterpret_cast<const float4*>(h0 + size_t(r) * N) + tid;             // propagate.comp:43
         const float4* __restrict__ pr = reinterpret_cast<const float4*>(h0 + size_t(N - 1 - r) * N + N) - 1 - tid;   // :48
         const float2* __restrict__ pw = reinterpret_cast<const float2*>(omega + size_t(r) * N) + tid;
         const float2* __restrict__ pk = reinterpret_cast<const float2*>(kx_g) + tid;
         // kx_g[g] = pi32 * float(uint(2g - N - 1)) / L, tabulated on the host with the shader's fp32 ops
         const float ky = __ldg(kx_g + r);
-        const bool last_valid = !TAIL || tid + (ITER - 1) * NT < N / 2;
         float4 a[ITER], b[ITER];
         float2 w[ITER], kx[ITER];
 #pragma unroll
         for (int u = 0; u < ITER; ++u) {
-            const int uu = (u == ITER - 1 && !last_valid) ? 0 : u;       // clamp instead of branching; result unused
-            a[u] = __ldg(pf + uu * NT);
-            b[u] = __ldg(pr - uu * NT);             // .zw is the partner of x, .xy the partner of x + 1
-            w[u] = __ldg(pw + uu * NT);
-            kx[u] = __ldg(pk + uu * NT);
+            if (tid + u * NT < N / 2) {
+                a[u] = __ldg(pf + u * NT);
+                b[u] = __ldg(pr - u * NT);          // .zw is the partner of x, .xy the partner of x + 1
+                w[u] = __ldg(pw + u * NT);
+                kx[u] = __ldg(pk + u * NT);
+            }
         }
-        float wmax = 0.f;
-#pragma unroll
-        for (int u = 0; u < ITER; ++u) wmax = fmaxf(wmax, fmaxf(fabsf(w[u].x), fabsf(w[u].y)));
         float4* row = S + slot * SP;
-        if (wmax * fabsf(time) <= 0.99e5f) {
 #pragma unroll
-            for (int u = 0; u < ITER; ++u) {
+        for (int u = 0; u < ITER; ++u) {
+            if (tid + u * NT < N / 2) {
                 const int x = 2 * (tid + u * NT);
-                const float2 h_0 = propagate_point_reduced(make_float2(a[u].x, a[u].y), make_float2(b[u].z, b[u].w), w[u].x, time);
-                const float2 h_1 = propagate_point_reduced(make_float2(a[u].z, a[u].w), make_float2(b[u].x, b[u].y), w[u].y, time);
+                const float2 h_0 = propagate_point_fast(make_float2(a[u].x, a[u].y), make_float2(b[u].z, b[u].w), w[u].x, time);
+                const float2 h_1 = propagate_point_fast(make_float2(a[u].z, a[u].w), make_float2(b[u].x, b[u].y), w[u].y, time);
                 const float2 k_0 = unit_wave_vector_fast(kx[u].x, ky);
                 const float2 k_1 = unit_wave_vector_fast(kx[u].y, ky);
-                if (u < ITER - 1 || last_valid) {
-                    row[x] = make_float4(h_0.x, h_0.y, k_0.x, k_0.y);
-                    row[x + 1] = make_float4(h_1.x, h_1.y, k_1.x, k_1.y);
-                    if (x == 0) row[N] = make_float4(h_0.x, h_0.y, k_0.x, k_0.y);
-                }
+                row[x] = make_float4(h_0.x, h_0.y, k_0.x, k_0.y);
+                row[x + 1] = make_float4(h_1.x, h_1.y, k_1.x, k_1.y);
+                if (x == 0) row[N] = make_float4(h_0.x, h_0.y, k_0.x, k_0.y);
             }
-        } else {
-            propagate_row_general(h0, omega, kx_g, r, N, time, tid, NT, row);
         }
     }
     __syncthreads();

@@ -111,15 +111,6 @@ __device__ __forceinline__ void sincos_full(float x, float& sn, float& cs)
     }
 }
 
-// Branch-free propagate for callers that have already established |omega * t| <= 1e5 for every point
-// they handle (straight-line code lets the scheduler interleave the independent point chains).
-__device__ __forceinline__ float2 propagate_point_reduced(float2 a, float2 b, float omega, float time)
-{
-    float s, c;
-    sincos_reduced(__fmul_rn(omega, time), s, c);
-    return make_float2((a.x + b.x) * c - (a.y - b.y) * s, (a.y + b.y) * c + (a.x - b.x) * s);
-}
-
 // Same as propagate_point with the sincos above.
 __device__ __forceinline__ float2 propagate_point_fast(float2 a, float2 b, float omega, float time)
 {
