@@ -62,6 +62,9 @@ extern "C" {
     pub fn ocean_update(ctx: *mut ocean_ctx, time: f32) -> c_int;
     pub fn ocean_update_tiles(ctx: *mut ocean_ctx, time: f32, first_tile: u32, count: u32) -> c_int;
     pub fn ocean_update_sequence(ctx: *mut ocean_ctx, t0: f32, dt: f32, n_frames: u32) -> c_int;
+    pub fn ocean_compute_normals(ctx: *mut ocean_ctx, first_tile: u32, count: u32) -> c_int;
+    pub fn ocean_normals_device(ctx: *mut ocean_ctx, tile: u32, d_nrm: *mut *const f32) -> c_int;
+    pub fn ocean_download_normals(ctx: *mut ocean_ctx, tile: u32, h_nrm: *mut f32) -> c_int;
     pub fn ocean_profile_update(ctx: *mut ocean_ctx, time: f32, stage_ms: *mut f32, capacity: u32, n_stages: *mut u32) -> c_int;
     pub fn ocean_output_device(ctx: *mut ocean_ctx, tile: u32, d_rgba: *mut *const f32) -> c_int;
     pub fn ocean_download(ctx: *mut ocean_ctx, tile: u32, h_rgba: *mut f32) -> c_int;

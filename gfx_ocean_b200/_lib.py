@@ -56,6 +56,9 @@ SIGNATURES = {
     "ocean_download_async": (C.c_int, [_P, _U32, _P]),
     "ocean_sync": (C.c_int, [_P]),
     "ocean_debug_spectra": (C.c_int, [_P, _U32, _P, _P, _P]),
+    "ocean_compute_normals": (C.c_int, [_P, _U32, _U32]),
+    "ocean_normals_device": (C.c_int, [_P, _U32, C.POINTER(_P)]),
+    "ocean_download_normals": (C.c_int, [_P, _U32, _P]),
     "ocean_profile_update": (C.c_int, [_P, _F, _FP, _U32, C.POINTER(_U32)]),
     "ocean_get_locals": (C.c_int, [_P, C.POINTER(PropagateLocals), C.POINTER(CorrectionLocals)]),
     "ocean_resolution": (_U32, [_P]),

@@ -14,6 +14,8 @@ cudaError_t launch_fft_col_literal(float2* data, uint32_t n, cudaStream_t s);
 cudaError_t launch_correction_literal(const float2* height, const float2* dx, const float2* dz,
                                       uint32_t n, float4* out, cudaStream_t s);
 bool literal_supports(uint32_t n);
+// shader/ocean.frag:50-66 at texel centres; disp/out: [tiles][N][N] float4
+cudaError_t launch_normal_map(const float4* disp, float4* nrm, uint32_t n, uint32_t tiles, cudaStream_t s);
 
 // ---- fused pipeline: k_rows + k_cols (kernels_fused.cu)
 struct FusedPlan;

@@ -36,6 +36,8 @@ struct ocean_ctx {
     void* d_work = nullptr;
     size_t work_bytes = 0;
     ocean::FusedPlan* plan = nullptr;
+    // normal map of the consumer step (lazy), float4[tile][y][x]
+    float4* d_nrm = nullptr;
     // ocean_debug_spectra scratch (lazy)
     float2* d_dbg = nullptr;
 
@@ -215,6 +217,7 @@ void ocean_destroy(ocean_ctx* c)
     cudaFree(c->d_spec);
     cudaFree(c->d_work);
     cudaFree(c->d_dbg);
+    cudaFree(c->d_nrm);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     (void)cudaGetLastError();
     delete c;
@@ -309,6 +312,39 @@ int ocean_update_sequence(ocean_ctx* c, float t0, float dt, uint32_t n_frames)
     if (!c) return OCEAN_ERR_INVALID_ARG;
     for (uint32_t i = 0; i < n_frames; ++i)
         if (int rc = ocean_update_tiles(c, t0 + dt * float(i), 0, c->n_tiles)) return rc;
+    return OCEAN_OK;
+}
+
+int ocean_compute_normals(ocean_ctx* c, uint32_t first_tile, uint32_t count)
+{
+    if (!c) return OCEAN_ERR_INVALID_ARG;
+    if (count == 0 || first_tile >= c->n_tiles || count > c->n_tiles - first_tile)
+        return fail(c, OCEAN_ERR_INVALID_ARG, "tile range out of bounds");
+    if (!c->updated) return fail(c, OCEAN_ERR_NOT_READY, "ocean_update has not been called");
+    OCEAN_CUDA(c, cudaSetDevice(c->device));
+    if (!c->d_nrm) OCEAN_CUDA(c, cudaMalloc(&c->d_nrm, size_t(c->n_tiles) * pts(c) * sizeof(float4)));
+    OCEAN_CUDA(c, ocean::launch_normal_map(c->d_out + first_tile * pts(c), c->d_nrm + first_tile * pts(c), c->n, count, c->stream));
+    c->launches += 1;
+    return OCEAN_OK;
+}
+
+int ocean_normals_device(ocean_ctx* c, uint32_t tile, const float** d_nrm)
+{
+    if (int rc = check_tile(c, tile)) return rc;
+    if (!d_nrm) return fail(c, OCEAN_ERR_INVALID_ARG, "null output pointer");
+    if (!c->d_nrm) return fail(c, OCEAN_ERR_NOT_READY, "ocean_compute_normals has not been called");
+    *d_nrm = reinterpret_cast<const float*>(c->d_nrm + tile * pts(c));
+    return OCEAN_OK;
+}
+
+int ocean_download_normals(ocean_ctx* c, uint32_t tile, float* h_nrm)
+{
+    if (int rc = check_tile(c, tile)) return rc;
+    if (!h_nrm) return fail(c, OCEAN_ERR_INVALID_ARG, "null output pointer");
+    if (!c->d_nrm) return fail(c, OCEAN_ERR_NOT_READY, "ocean_compute_normals has not been called");
+    OCEAN_CUDA(c, cudaSetDevice(c->device));
+    OCEAN_CUDA(c, cudaMemcpyAsync(h_nrm, c->d_nrm + tile * pts(c), pts(c) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    OCEAN_CUDA(c, cudaStreamSynchronize(c->stream));
     return OCEAN_OK;
 }
 

@@ -111,6 +111,21 @@ class Ocean:
     def read_back_async(self, tile: int, host_ptr: int) -> None:
         self._check(self._lib.ocean_download_async(self._ctx, tile, host_ptr))
 
+    # -- consumer step: the normal map of shader/ocean.frag:50-66 ----------------------------------
+    def compute_normals(self, first_tile: int = 0, count: int | None = None) -> None:
+        self._check(self._lib.ocean_compute_normals(self._ctx, first_tile, self.n_tiles - first_tile if count is None else count))
+
+    def normals(self, tile: int = 0) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.ocean_normals_device(self._ctx, tile, C.byref(p)))
+        return p.value
+
+    def read_back_normals(self, tile: int = 0) -> np.ndarray:
+        n = self.resolution
+        out = np.empty((n, n, 4), np.float32)
+        self._check(self._lib.ocean_download_normals(self._ctx, tile, out.ctypes.data))
+        return out
+
     def debug_spectra(self, tile: int = 0):
         n = self.resolution
         outs = [np.empty((n, n, 2), np.float32) for _ in range(3)]

@@ -119,6 +119,14 @@ OCEAN_API int  ocean_download(ocean_ctx* ctx, uint32_t tile, float* h_rgba);
 OCEAN_API int  ocean_download_async(ocean_ctx* ctx, uint32_t tile, float* h_rgba);
 OCEAN_API int  ocean_sync(ocean_ctx* ctx);
 
+/* ---- consumer step (what the renderer derives from the map) */
+/* Enqueue the normal map of shader/ocean.frag:50-66 for tiles [first_tile, first_tile+count): central
+ * differences of channel .x over wrapped neighbours (sampler Linear/Tile, src/render.rs:398), diff = 2/N,
+ * height_scale = 180; texel = (N.x, N.y, N.z, 0). Reads the displacement map of the last ocean_update. */
+OCEAN_API int  ocean_compute_normals(ocean_ctx* ctx, uint32_t first_tile, uint32_t count);
+OCEAN_API int  ocean_normals_device(ocean_ctx* ctx, uint32_t tile, const float** d_nrm /* N*N*4 */);
+OCEAN_API int  ocean_download_normals(ocean_ctx* ctx, uint32_t tile, float* h_nrm /* N*N*4 */);   /* waits */
+
 /* ---- measurement */
 /* One update with CUDA events recorded on the context's stream around every kernel of the frame;
  * waits, then writes each kernel's duration in ms (FUSED: [k_rows, k_cols]; LITERAL: the 8

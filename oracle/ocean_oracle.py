@@ -63,6 +63,9 @@ class COracle:
             f = getattr(self.lib, f"oracle_correction_{suf}")
             f.argtypes = [rp, rp, rp, C.c_uint32, rp]
             f.restype = None
+            f = getattr(self.lib, f"oracle_normal_map_{suf}")
+            f.argtypes = [rp, C.c_uint32, rp]
+            f.restype = None
             f = getattr(self.lib, f"oracle_frame_{suf}")
             f.argtypes = [_f32p, _f32p, C.c_float, C.c_uint32, C.c_float, rp]
             f.restype = C.c_int
@@ -116,6 +119,15 @@ class COracle:
                                                        float(domain_size), out)
         if rc != 0:
             raise ValueError(f"oracle_frame_{prec} failed rc={rc} (N must be a power of two)")
+        return out.reshape(n, n, 4)
+
+    def normal_map(self, disp, prec="f64"):
+        """shader/ocean.frag:50-66 at texel centres: disp[N, N, 4] -> normals[N, N, 4] = (N.x, N.y, N.z, 0)."""
+        dt = self._dt(prec)
+        d = np.ascontiguousarray(disp, dt)
+        n = d.shape[0]
+        out = np.empty(n * n * 4, dt)
+        getattr(self.lib, f"oracle_normal_map_{prec}")(d.reshape(-1), n, out)
         return out.reshape(n, n, 4)
 
     def read_bincode(self, path: str, elem_floats: int, capacity: int) -> np.ndarray:
@@ -181,6 +193,22 @@ def frame_np(h0, omega, time, n, domain_size=1000.0):
     h, dx, dz = propagate_np(h0, omega, time, n, domain_size)
     s = float(n * n)
     return correction_np(np.fft.ifft2(h) * s, np.fft.ifft2(dx) * s, np.fft.ifft2(dz) * s)
+
+
+def normal_map_np(disp):
+    """Independent numpy formulation of shader/ocean.frag:50-66 at texel centres (Tile wrap)."""
+    d = np.asarray(disp, np.float64)[..., 0]
+    n = d.shape[0]
+    diff, hs = 2.0 / n, 180.0
+    dxv = (np.roll(d, -1, axis=1) - np.roll(d, 1, axis=1)) / hs
+    dzv = (np.roll(d, -1, axis=0) - np.roll(d, 1, axis=0)) / hs
+    na = np.stack([np.full_like(d, -diff), dxv, np.zeros_like(d)], -1)
+    nb = np.stack([np.zeros_like(d), dzv, np.full_like(d, diff)], -1)
+    na /= np.linalg.norm(na, axis=-1, keepdims=True)
+    nb /= np.linalg.norm(nb, axis=-1, keepdims=True)
+    c = np.cross(na, nb)
+    c /= np.linalg.norm(c, axis=-1, keepdims=True)
+    return np.concatenate([c, np.zeros(d.shape + (1,))], -1)
 
 
 def stockham_line_np(x: np.ndarray, pi=float(PI32)) -> np.ndarray:

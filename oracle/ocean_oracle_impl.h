@@ -227,6 +227,45 @@ void NAME(correction)(const REAL *height, const REAL *disp_x, const REAL *disp_z
     }
 }
 
+/* Consumer step: the "lazy" normal map of shader/ocean.frag:50-66 evaluated at the
+ * texel centres of the displacement map (sampler: Linear filter, Tile wrap, src/render.rs:398, so a one-texel
+ * textureOffset at a texel centre is the wrapped neighbour). It differentiates channel .x (the dx displacement),
+ * as the shader does; `diff = 2.0 / dim` with dim hard-coded to 512 there (":50 TODO textureSize") is 2/N here.
+ *   na = normalize(-diff, (x1-x0)/height_scale, 0), nb = normalize(0, (z1-z0)/height_scale, diff),
+ *   N = normalize(cross(na, nb)); height_scale = 180 (:19). out = (N.x, N.y, N.z, 0). */
+void NAME(normal_map)(const REAL *disp_rgba /* N*N*4 */, uint32_t n, REAL *out_nrm /* N*N*4 */)
+{
+    const REAL diff = (REAL)2.0 / (REAL)n;
+    const REAL height_scale = (REAL)180.0;
+#pragma omp parallel for schedule(static)
+    for (int64_t y_ = 0; y_ < (int64_t)n; ++y_) {
+        const uint32_t y = (uint32_t)y_;
+        for (uint32_t x = 0; x < n; ++x) {
+            const REAL x0 = disp_rgba[4 * ((size_t)((x + n - 1) % n) + (size_t)n * y)];
+            const REAL x1 = disp_rgba[4 * ((size_t)((x + 1) % n) + (size_t)n * y)];
+            const REAL z0 = disp_rgba[4 * ((size_t)x + (size_t)n * ((y + n - 1) % n))];
+            const REAL z1 = disp_rgba[4 * ((size_t)x + (size_t)n * ((y + 1) % n))];
+            REAL nax = -diff, nay = (x1 - x0) / height_scale;
+            REAL nby = (z1 - z0) / height_scale, nbz = diff;
+#if REAL_IS_DOUBLE
+            const REAL la = sqrt(nax * nax + nay * nay), lb = sqrt(nby * nby + nbz * nbz);
+#else
+            const REAL la = sqrtf(nax * nax + nay * nay), lb = sqrtf(nby * nby + nbz * nbz);
+#endif
+            nax /= la; nay /= la; nby /= lb; nbz /= lb;
+            /* cross((nax, nay, 0), (0, nby, nbz)) */
+            REAL cx = nay * nbz, cy = -nax * nbz, cz = nax * nby;
+#if REAL_IS_DOUBLE
+            const REAL lc = sqrt(cx * cx + cy * cy + cz * cz);
+#else
+            const REAL lc = sqrtf(cx * cx + cy * cy + cz * cz);
+#endif
+            REAL *o = out_nrm + 4 * ((size_t)x + (size_t)n * y);
+            o[0] = cx / lc; o[1] = cy / lc; o[2] = cz / lc; o[3] = (REAL)0.0;
+        }
+    }
+}
+
 /* src/render.rs:1122-1287: propagate; barrier; row pass on dx,dy,dz; barrier;
  * col pass on dx,dy,dz; barrier; correction. work = 3 * N*N*2 REALs of scratch. */
 int NAME(frame)(const float *h0, const float *omega, float time, uint32_t n,

@@ -175,6 +175,22 @@ def test_linearity_and_real_transform_roundtrip_1024(oracle):
     del hs
 
 
+def test_normal_map_matches_oracle(shipped_fused, oracle):
+    """Consumer step: shader/ocean.frag:50-66 at texel centres, from the GPU's own map."""
+    shipped_fused.update(2.5)
+    disp = shipped_fused.read_back()
+    shipped_fused.compute_normals()
+    nrm = shipped_fused.read_back_normals()
+    ref = oracle.normal_map(disp.astype(np.float64), prec="f64")
+    assert np.abs(nrm - ref).max() <= 1e-5
+    np.testing.assert_allclose(np.linalg.norm(nrm[..., :3], axis=-1), 1.0, atol=1e-5)
+    assert np.all(nrm[..., 3] == 0.0)
+    with Ocean(256) as o:
+        with pytest.raises(OceanError) as e:
+            o.compute_normals()
+        assert e.value.status == _lib.ERR_NOT_READY
+
+
 def test_error_behaviour(tmp_path):
     with Ocean(256) as o:
         with pytest.raises(OceanError) as e:

@@ -168,3 +168,21 @@ def test_smallest_grid(oracle):
     w = np.array([[0.5, 1.0], [1.5, 2.0]], np.float32)
     out = oracle.frame(h0, w, 0.7, 2, prec="f64")
     assert max(max_rel_err(frame_np(h0, w, 0.7, 2), out)) < 1e-6
+
+
+def test_normal_map_c_vs_numpy_twin(oracle, ref_inputs):
+    """Consumer step (shader/ocean.frag:50-66 at texel centres): C restatement vs numpy formulation."""
+    from oracle.ocean_oracle import normal_map_np
+    sp, om = ref_inputs
+    disp = oracle.frame(sp, om, 1.0, 512, prec="f64")
+    nc = oracle.normal_map(disp, prec="f64")
+    nn = normal_map_np(disp)
+    np.testing.assert_allclose(nc, nn, atol=1e-13)
+    np.testing.assert_allclose(np.linalg.norm(nc[..., :3], axis=-1), 1.0, atol=1e-12)
+    assert np.all(nc[..., 3] == 0.0)
+    # a flat map has the normal cross((-1,0,0),(0,0,1)) = (0, 1, 0)
+    flat = oracle.normal_map(np.zeros((8, 8, 4)), prec="f64")
+    np.testing.assert_allclose(flat[..., :3], np.broadcast_to([0.0, 1.0, 0.0], (8, 8, 3)), atol=1e-15)
+    # fp32 literal restatement within 1e-6
+    n32 = oracle.normal_map(disp.astype(np.float32), prec="f32")
+    assert np.abs(n32 - nc).max() < 2e-6
