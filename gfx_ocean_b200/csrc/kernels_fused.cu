@@ -398,11 +398,11 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
     float2* TW = reinterpret_cast<float2*>(smem_raw + 2 * CC::P_BYTES + CC::H_BYTES + CC::XH_BYTES);   // [R1][R2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * CC::P_BYTES + CC::H_BYTES + CC::XH_BYTES + CC::TW_BYTES);
     uint64_t* fullP = bars;        // [2] GP strip landed in PB[b]               (tx bytes)         producer -> packed
-    uint64_t* drainedP = bars + 2; // [2] packed warps hold PB[b] in registers   (NTP/32 arrivals)  packed -> height
-    uint64_t* hrFree = bars + 4;   // [2] packed warps done with HR in PB[b]     (NTP/32 arrivals)  packed -> producer
+    uint64_t* drainedP = bars + 2; // [2] packed warps hold PB[b] in registers   (NTP arrivals)     packed -> height
+    uint64_t* hrFree = bars + 4;   // [2] packed warps done with HR in PB[b]     (NTP arrivals)     packed -> producer
     uint64_t* fullG = bars + 6;    //     GH strip landed                        (tx bytes)         producer -> height
-    uint64_t* emptyG = bars + 7;   //     height warps drained GB                (NTH/32 arrivals)  height -> producer
-    uint64_t* hrReady = bars + 8;  //     HR written into PB[b]                  (NTH/32 arrivals)  height -> packed
+    uint64_t* emptyG = bars + 7;   //     height warps drained GB                (NTH arrivals)     height -> producer
+    uint64_t* hrReady = bars + 8;  //     HR written into PB[b]                  (NTH arrivals)     height -> packed
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -411,13 +411,13 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
     if (tid == 0) {
         ptx::mbar_init(fullP + 0, 1);
         ptx::mbar_init(fullP + 1, 1);
-        ptx::mbar_init(drainedP + 0, NTP / 32);
-        ptx::mbar_init(drainedP + 1, NTP / 32);
-        ptx::mbar_init(hrFree + 0, NTP / 32);
-        ptx::mbar_init(hrFree + 1, NTP / 32);
+        ptx::mbar_init(drainedP + 0, NTP);
+        ptx::mbar_init(drainedP + 1, NTP);
+        ptx::mbar_init(hrFree + 0, NTP);
+        ptx::mbar_init(hrFree + 1, NTP);
         ptx::mbar_init(fullG, 1);
-        ptx::mbar_init(emptyG, NTH / 32);
-        ptx::mbar_init(hrReady, NTH / 32);
+        ptx::mbar_init(emptyG, NTH);
+        ptx::mbar_init(hrReady, NTH);
         ptx::fence_mbar_init();
     }
     __syncthreads();
@@ -487,8 +487,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                     else v[k1] = make_float2(g.x + g.w, g.z - g.y);
                 }
             }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(emptyG);
+            ptx::mbar_arrive(emptyG);
             RegFft<R1>::run(v);
 #pragma unroll
             for (int n1 = 1; n1 < R1; ++n1) v[n1] = cmul_tw(v[n1], TW[n1 * T + k2]);
@@ -529,8 +528,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                 (void)waited;
                 ptx::named_bar_sync<2, NTH>();                          // XH drained: the next item may overwrite it
             }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(hrReady);
+            ptx::mbar_arrive(hrReady);
         }
     } else {
         // ================= packed (dx, dz) warps =================
@@ -563,8 +561,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
 #pragma unroll
                     for (int k = 0; k < R2; ++k) u[i][k] = PB[n1 * IL::GROUP_PITCH + k * C + c];
                 }
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(drainedP + b);
+                ptx::mbar_arrive(drainedP + b);
 #pragma unroll
                 for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2>::run(u[i]);
                 ptx::mbar_wait(hrReady, it & 1);
@@ -602,8 +599,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                     for (int k = 0; k < R3; ++k) w[i][k] = PB[IL::row_off(n1 * T + n2 * R3 + k) + c];
                     RegFft<R3>::run(w[i]);
                 }
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(drainedP + b);
+                ptx::mbar_arrive(drainedP + b);
                 ptx::mbar_wait(hrReady, it & 1);
 #pragma unroll
                 for (int i = 0; i < Cfg::SUB3; ++i) {
@@ -617,8 +613,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                 }
             }
             ptx::fence_proxy_async();          // generic-proxy accesses to PB[b] precede the next bulk copy into it
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(hrFree + b);
+            ptx::mbar_arrive(hrFree + b);
         }
     }
 }
