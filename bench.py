@@ -256,6 +256,27 @@ def main():
                   "alg_GBps": ALG_BYTES_PER_POINT * n * n / (ms1 / ks * 1e-3) / 1e9,
                   "note": "one tile per ocean_update (2 launches), rotating over the tiles so inputs are L2-cold"}
 
+    # ---- library sanity bar: cuFFT's batched 2-D C2C inverse transform ALONE on the same
+    #      amount of data (3 complex fields per tile, via torch.fft.ifft2), without propagate or correction.
+    #      A comparison line only: nothing of it is on the product path.
+    cufft_ms = None
+    if rank == 0:
+        try:
+            spec = torch.randn(len(my_tiles) * 3, n, n, dtype=torch.complex64, device="cuda")
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    torch.fft.ifft2(spec, norm="forward")
+                torch.cuda.synchronize()
+                ev0.record(stream)
+                for _ in range(20):
+                    torch.fft.ifft2(spec, norm="forward")
+                ev1.record(stream)
+                torch.cuda.synchronize()
+            cufft_ms = ev0.elapsed_time(ev1) / 20
+            del spec
+        except Exception as exc:      # comparison only
+            cufft_ms = f"unavailable: {exc}"
+
     # ---- per-kernel durations (CUDA events between the two launches, same stream)
     stage_ms = None
     if args.pipeline == "fused":
@@ -305,6 +326,7 @@ def main():
                     "steps": e2e_steps, "note": "Ocean.update(t) + read_back of every tile into pinned host memory + sync, per step"},
             "step_alg_GBps": alg_step / (ms / K * 1e-3) / 1e9,
             "single_tile_per_update": single,
+            "cufft_ifft2_only_ms_per_step": cufft_ms,
         }
         if stage_ms:
             alg = [ALG_BYTES_ROWS * n * n * len(my_tiles), ALG_BYTES_COLS * n * n * len(my_tiles)]
