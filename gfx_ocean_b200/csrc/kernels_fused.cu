@@ -689,6 +689,8 @@ struct Launch {
     }
 };
 
+using L64 = Launch<64, 8, 4, 8, 4>;       // small grids: 8 x 8 and 16 x 8 lines, several row pairs per block
+using L128 = Launch<128, 16, 4, 8, 4>;
 using L256 = Launch<256, 16, 2, 8, 4>;
 using L512 = Launch<512, 32, 2, 8, 4>;
 using L2048 = Launch<2048, 32, 1, 4, 2>;   // three-pass lines (32 x 32 x 2), strips of 4 columns
@@ -702,7 +704,7 @@ using L2048 = Launch<2048, 32, 1, 4, 2>;   // three-pass lines (32 x 32 x 2), st
 #endif
 using L1024 = Launch<1024, 32, OCEAN_ROWS_PAIRS_1024, 8, OCEAN_ROWS_MINB_1024>;
 
-bool fused_supports(uint32_t n) { return n == 256 || n == 512 || n == 1024 || n == 2048; }
+bool fused_supports(uint32_t n) { return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048; }
 
 // pass-1 twiddles w_N^(n1 t) as [R1][T], then pass-2 twiddles w_T^(n2 k3) as [R2][R3]
 template <class Cfg>
@@ -738,6 +740,8 @@ cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, flo
 
     std::vector<float2> tw;
     switch (n) {
+        case 64: tw = make_twiddles<L64::Cfg>(); break;
+        case 128: tw = make_twiddles<L128::Cfg>(); break;
         case 256: tw = make_twiddles<L256::Cfg>(); break;
         case 512: tw = make_twiddles<L512::Cfg>(); break;
         case 1024: tw = make_twiddles<L1024::Cfg>(); break;
@@ -756,6 +760,8 @@ cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, flo
     if ((e = cudaMemcpy(p->d_kx, kx.data(), n * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e);
     size_t gp_t, gh_t;
     switch (n) {
+        case 64: gp_t = L64::gp_floats2_per_tile(); gh_t = L64::gh_floats2_per_tile(); e = L64::prepare(p); break;
+        case 128: gp_t = L128::gp_floats2_per_tile(); gh_t = L128::gh_floats2_per_tile(); e = L128::prepare(p); break;
         case 256: gp_t = L256::gp_floats2_per_tile(); gh_t = L256::gh_floats2_per_tile(); e = L256::prepare(p); break;
         case 512: gp_t = L512::gp_floats2_per_tile(); gh_t = L512::gh_floats2_per_tile(); e = L512::prepare(p); break;
         case 1024: gp_t = L1024::gp_floats2_per_tile(); gh_t = L1024::gh_floats2_per_tile(); e = L1024::prepare(p); break;
@@ -786,6 +792,8 @@ cudaError_t fused_enqueue(FusedPlan* p, const float2* h0, const float* omega, fl
 {
     cudaError_t e;
     switch (p->n) {
+        case 64: e = L64::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
+        case 128: e = L128::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
         case 256: e = L256::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
         case 512: e = L512::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
         case 1024: e = L1024::run(p, h0, omega, out, time, first_tile, count, s, ev); break;

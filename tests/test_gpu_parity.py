@@ -86,7 +86,7 @@ def test_fused_and_literal_agree(shipped_fused, shipped_literal):
     assert max(max_rel_err(a, b)) <= 5e-6
 
 
-@pytest.mark.parametrize("n", [256, 1024, 2048])
+@pytest.mark.parametrize("n", [64, 128, 256, 1024, 2048])
 @pytest.mark.parametrize("t", [0.0, 1.0, 37.5])
 def test_synthetic_tiles_match_oracle(n, t, oracle):
     """BASELINE.json configs 3/4: seeded synthetic grids at other resolutions
@@ -208,6 +208,17 @@ def test_error_behaviour(tmp_path):
     with pytest.raises(OceanError) as e:
         Ocean(512, device=99)
     assert e.value.status == _lib.ERR_NO_DEVICE
+
+
+def test_unsupported_resolutions_fail_loudly():
+    """The fused pipeline covers N in {64 .. 2048}; anything else is an error, never a silent fallback."""
+    for n in (8, 32, 4096):
+        with pytest.raises(OceanError) as e:
+            Ocean(n)
+        assert e.value.status == _lib.ERR_UNSUPPORTED
+    with pytest.raises(OceanError) as e:
+        Ocean(4096, pipeline=PIPELINE_LITERAL)
+    assert e.value.status == _lib.ERR_UNSUPPORTED
 
 
 def test_zero_spectrum_gives_zero_field():
