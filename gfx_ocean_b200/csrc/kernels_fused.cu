@@ -132,7 +132,7 @@ template <int N, int P, int PAIRS, int C, int MINB>
 __global__ void __launch_bounds__(3 * PAIRS * (N / P), MINB)
 k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, const float2* __restrict__ tw_g,
        const float* __restrict__ kx_g, float2* __restrict__ gp_all, float2* __restrict__ gh_all, float time,
-       uint32_t first_tile)
+       uint32_t first_tile, uint32_t resident_blocks)
 {
     using Cfg = LineCfg<N, P>;
     constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2;
@@ -251,8 +251,10 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
         line[Cfg::pad(n1 * T + k2)] = y;
     }
     if constexpr (T <= 32) __syncwarp(); else __syncthreads();
-    // the intermediate is still being read by the previous frame's k_cols until that grid has completed
-    pdl_wait_prior_grid();
+    // The intermediate is still being read by the previous frame's k_cols until that grid has completed. Only
+    // blocks that can be resident before any block of this grid has exited need to wait: every later block
+    // starts after an earlier one has passed this point (griddepcontrol.wait costs ~0.3 us even when satisfied).
+    if (blockIdx.x + gridDim.x * blockIdx.y < resident_blocks) pdl_wait_prior_grid();
 
     // Destination row in the strip-major intermediate. Thread n1 owns columns n = n1 + R1 n2: strip n / C and
     // in-strip column n % C advance by a constant per n2 (R1 is a multiple of C), also for the mirrored
@@ -626,6 +628,7 @@ struct FusedPlan {
     float domain_size = 0.f;
     int num_sms = 0;
     int cols_blocks_per_sm = 1;  // persistent k_cols blocks resident per SM
+    int rows_blocks_per_sm = 1;  // k_rows blocks resident per SM (occupancy)
     int pdl_mode = -1;           // programmatic dependent launch: -1 auto (small grids), 0 off, 1 on (env OCEAN_B200_PDL)
     float2* d_tw = nullptr;      // [R1][R2] inter-pass twiddles
     float* d_kx = nullptr;       // [N] wave numbers, propagate.comp:45-46,50-53
@@ -649,6 +652,9 @@ struct Launch {
         int per_sm = 1;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cols<N, P, C>, CC::NTHREADS, CC::SMEM);
         p->cols_blocks_per_sm = per_sm < 1 ? 1 : per_sm;
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rows<N, P, PAIRS, C, MINB>, 3 * PAIRS * Cfg::T, smem_rows);
+        p->rows_blocks_per_sm = per_sm < 1 ? 1 : per_sm;
         return e;
     }
     static size_t gp_floats2_per_tile() { return IL::P_TILE; }
@@ -674,7 +680,8 @@ struct Launch {
         const float2* tw = p->d_tw;
         const float* kx = p->d_kx;
         float2 *gp = p->d_gp, *gh = p->d_gh;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_rows<N, P, PAIRS, C, MINB>, h0, omega, tw, kx, gp, gh, time, first_tile);
+        const uint32_t resident = uint32_t(p->num_sms * p->rows_blocks_per_sm);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_rows<N, P, PAIRS, C, MINB>, h0, omega, tw, kx, gp, gh, time, first_tile, resident);
         if (e != cudaSuccess) return e;
         if (ev) cudaEventRecord(ev[1], s);
         const uint32_t items = count * (N / C);
