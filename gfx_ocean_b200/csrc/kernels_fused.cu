@@ -709,7 +709,10 @@ using L2048 = Launch<2048, 32, 1, 4, 2>;   // three-pass lines (32 x 32 x 2), st
 #ifndef OCEAN_ROWS_MINB_1024
 #define OCEAN_ROWS_MINB_1024 5
 #endif
-using L1024 = Launch<1024, 32, OCEAN_ROWS_PAIRS_1024, 8, OCEAN_ROWS_MINB_1024>;
+#ifndef OCEAN_STRIP_1024
+#define OCEAN_STRIP_1024 8           // 4-column strips (two k_cols blocks per SM) measured 10 % slower
+#endif
+using L1024 = Launch<1024, 32, OCEAN_ROWS_PAIRS_1024, OCEAN_STRIP_1024, OCEAN_ROWS_MINB_1024>;
 
 bool fused_supports(uint32_t n) { return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048; }
 
