@@ -227,6 +227,56 @@ def test_zero_spectrum_gives_zero_field():
         assert not o.read_back().any()
 
 
+def test_two_contexts_interleaved_and_threaded(oracle):
+    """Contexts are independent (own stream, own buffers): interleaving them, or driving them from two host
+    threads, gives the same frames as running them alone (SURVEY.md 8b threading row)."""
+    import threading
+    n = 256
+    data = [synthetic_tile(n, i) for i in (5, 6)]
+    refs = [oracle.frame(h0, w, 4.0, n, prec="f64") for h0, w in data]
+    ctxs = [Ocean.new(n, 1000.0, w, h0) for h0, w in data]
+    try:
+        for _ in range(3):                       # interleaved on one thread
+            for c in ctxs:
+                c.update(4.0)
+        outs = [c.read_back() for c in ctxs]
+        for o, r in zip(outs, refs):
+            assert max(max_rel_err(o, r)) <= TOL
+        results = [None, None]
+
+        def work(i):
+            for k in range(20):
+                ctxs[i].update(float(k))
+            ctxs[i].update(4.0)
+            results[i] = ctxs[i].read_back()
+        th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        for o, r in zip(results, outs):
+            assert np.array_equal(o, r)
+    finally:
+        for c in ctxs:
+            c.destroy()
+
+
+def test_external_stream_is_used():
+    """ocean_config.stream: the context enqueues on the caller's stream (here a torch stream)."""
+    import torch
+    s = torch.cuda.Stream()
+    h0, w = synthetic_tile(256, 1)
+    with Ocean(256, stream=s.cuda_stream) as o:
+        assert o.stream == s.cuda_stream
+        o.set_spectrum(0, h0, w)
+        ev = torch.cuda.Event()
+        o.update(1.0)
+        ev.record(s)
+        ev.synchronize()
+        a = o.read_back()
+    with Ocean.new(256, 1000.0, w, h0) as o2:
+        o2.update(1.0)
+        assert np.array_equal(o2.read_back(), a)
+
+
 def test_launch_accounting(shipped_fused, shipped_literal):
     a = shipped_fused.launch_count; shipped_fused.update(1.0); assert shipped_fused.launch_count - a == 2
     b = shipped_literal.launch_count; shipped_literal.update(1.0); assert shipped_literal.launch_count - b == 8
