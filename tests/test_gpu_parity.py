@@ -102,6 +102,16 @@ def test_synthetic_tiles_match_oracle(n, t, oracle):
     check_w_channel(out)
 
 
+@pytest.mark.parametrize("t", [-12.5, 3.0e4, 1.0e6])
+def test_negative_and_huge_times(t, oracle):
+    """Negative time, and phases far beyond 1e5 rad where every point takes the Payne-Hanek sincos path."""
+    h0, w = synthetic_tile(256, 7)
+    with Ocean.new(256, 1000.0, w, h0) as o:
+        o.update(t)
+        out = o.read_back()
+    assert max(max_rel_err(out, oracle.frame(h0, w, t, 256, prec="f64"))) <= TOL
+
+
 def test_golden_synth_1024(golden_synth):
     h0, w = synthetic_tile(1024, 0)
     with Ocean.new(1024, 1000.0, w, h0) as o:
