@@ -699,7 +699,15 @@ struct Launch {
 using L64 = Launch<64, 8, 4, 8, 4>;       // small grids: 8 x 8 and 16 x 8 lines, several row pairs per block
 using L128 = Launch<128, 16, 4, 8, 4>;
 using L256 = Launch<256, 16, 2, 8, 4>;
-using L512 = Launch<512, 32, 2, 8, 4>;
+// N=512 (the reference's own size): one row pair per block (48 threads), 8 blocks/SM at 128 registers measured
+// best of {1,2,4} pairs x {2..8} blocks (283 k frames/s batched, 122 k one tile per update)
+#ifndef OCEAN_ROWS_PAIRS_512
+#define OCEAN_ROWS_PAIRS_512 1
+#endif
+#ifndef OCEAN_ROWS_MINB_512
+#define OCEAN_ROWS_MINB_512 8
+#endif
+using L512 = Launch<512, 32, OCEAN_ROWS_PAIRS_512, 8, OCEAN_ROWS_MINB_512>;
 using L2048 = Launch<2048, 32, 1, 4, 2>;   // three-pass lines (32 x 32 x 2), strips of 4 columns
 // k_rows at N=1024: 5 blocks/SM (128 registers, no spills) measured faster than 6 blocks/SM at 96 registers
 // (68 vs 76 us per 8 tiles); overridable for A/B builds (scripts/ab_build.sh)
