@@ -39,7 +39,7 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    extra = os.environ.get("OCEAN_NVCC_EXTRA", "").split()      # e.g. -DOCEAN_SINCOS_SFU for A/B experiments
+    extra = os.environ.get("OCEAN_NVCC_EXTRA", "").split()      # extra -D flags for A/B builds (scripts/ab_build.sh)
     if not force and not extra and not _stale():
         return LIB
     objs = []

@@ -15,8 +15,8 @@
 // so nothing is read twice. Intermediate traffic is 12 B per grid point (GP: N x N complex,
 // GH: N/2 x N complex) instead of the reference's 24, and the butterflies are halved.
 //
-// Line transforms are 2-pass: N = R1 * R2, each thread owns P = R1 points in registers
-// (fft_reg.cuh), with one trip through padded shared memory between the passes.
+// Line transforms take two or three passes, N = R1 * R2 (* R3): each thread owns P = R1 points in
+// registers (fft_reg.cuh), with one trip through padded shared memory between passes (LineCfg).
 #include <cuda_runtime.h>
 
 #include <cmath>

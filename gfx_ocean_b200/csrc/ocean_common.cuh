@@ -83,27 +83,9 @@ __device__ __forceinline__ void sincos_reduced(float x, float& sn, float& cs)
     cs = ((q + 1) & 2) ? -co : co;
 }
 
-// Variant: reduce by pi (same three-step Cody-Waite, constants doubled exactly), then the SFU's
-// sin.approx / cos.approx on [-pi/2, pi/2] (abs error 2^-21.4 there) and a sign flip for odd multiples.
-__device__ __forceinline__ void sincos_reduced_sfu(float x, float& sn, float& cs)
-{
-    float j = fmaf(x, 0.318309873f, 12582912.f);      // rint(x / pi)
-    const uint32_t flip = uint32_t(__float_as_int(j)) << 31;
-    j -= 12582912.f;
-    float r = fmaf(j, -2.0f * 1.57079601e+00f, x);
-    r = fmaf(j, -2.0f * 3.13916473e-07f, r);
-    r = fmaf(j, -2.0f * 5.39030253e-15f, r);
-    sn = __int_as_float(__float_as_int(__sinf(r)) ^ flip);
-    cs = __int_as_float(__float_as_int(__cosf(r)) ^ flip);
-}
-
 __device__ __forceinline__ void sincos_full(float x, float& sn, float& cs)
 {
-#ifdef OCEAN_SINCOS_SFU
-    if (fabsf(x) <= 1.0e5f) sincos_reduced_sfu(x, sn, cs);
-#else
     if (fabsf(x) <= 1.0e5f) sincos_reduced(x, sn, cs);
-#endif
     else {
         const float2 sc = sincos_huge(x);
         sn = sc.x;
