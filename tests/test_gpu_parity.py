@@ -287,6 +287,36 @@ def test_external_stream_is_used():
         assert np.array_equal(o2.read_back(), a)
 
 
+def test_update_sequence_equals_the_last_update(shipped_fused):
+    shipped_fused.update_sequence(0.0, 0.5, 9)            # t = 0, 0.5, ..., 4.0
+    a = shipped_fused.read_back().copy()
+    shipped_fused.update(4.0)
+    assert np.array_equal(shipped_fused.read_back(), a)
+    assert shipped_fused.locals()[0].time == 4.0
+
+
+def test_create_destroy_does_not_leak_device_memory():
+    import torch
+    torch.cuda.synchronize()
+    h0, w = synthetic_tile(512, 0)
+    with Ocean.new(512, 1000.0, w, h0) as o:              # warm up lazy allocations of the runtime
+        o.update(0.0); o.compute_normals(); o.debug_spectra(); o.sync()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(20):
+        with Ocean.new(512, 1000.0, w, h0, n_tiles=2) as o:
+            o.update(1.0); o.compute_normals(); o.debug_spectra(); o.sync()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert abs(free0 - free1) <= 8 << 20                  # allocator granularity, not a per-context leak
+
+
+def test_soak_many_frames_stays_deterministic(shipped_fused):
+    shipped_fused.update(2.0)
+    a = shipped_fused.read_back().copy()
+    shipped_fused.update_sequence(0.0, 0.016, 3000)
+    shipped_fused.update(2.0)
+    assert np.array_equal(shipped_fused.read_back(), a)
+
+
 def test_launch_accounting(shipped_fused, shipped_literal):
     a = shipped_fused.launch_count; shipped_fused.update(1.0); assert shipped_fused.launch_count - a == 2
     b = shipped_literal.launch_count; shipped_literal.update(1.0); assert shipped_literal.launch_count - b == 8
