@@ -317,6 +317,28 @@ def test_soak_many_frames_stays_deterministic(shipped_fused):
     assert np.array_equal(shipped_fused.read_back(), a)
 
 
+def test_fuzz_sizes_tiles_ranges_and_times(oracle):
+    """Seeded sweep over resolution, tile count, partial tile ranges and time (both pipelines where legal)."""
+    rng = np.random.default_rng(20261017)
+    for case in range(14):
+        n = int(rng.choice([64, 128, 256, 512, 1024]))
+        n_tiles = int(rng.integers(1, 5))
+        first = int(rng.integers(0, n_tiles))
+        count = int(rng.integers(1, n_tiles - first + 1))
+        t = float(np.float32(rng.uniform(-100.0, 2000.0)))
+        pipeline = PIPELINE_LITERAL if case % 5 == 4 else PIPELINE_FUSED
+        tiles = [synthetic_tile(n, 100 + case * 8 + i) for i in range(n_tiles)]
+        with Ocean(n, 1000.0, n_tiles=n_tiles, pipeline=pipeline) as o:
+            for i, (h0, w) in enumerate(tiles):
+                o.set_spectrum(i, h0, w)
+            o.update(0.25)                                   # every tile gets a frame ...
+            o.update_tiles(t, first, count)                  # ... then only [first, first+count) moves to t
+            for i, (h0, w) in enumerate(tiles):
+                want_t = t if first <= i < first + count else 0.25
+                err = max(max_rel_err(o.read_back(i), oracle.frame(h0, w, want_t, n, prec="f64")))
+                assert err <= TOL, (case, n, n_tiles, first, count, t, i, err)
+
+
 def test_launch_accounting(shipped_fused, shipped_literal):
     a = shipped_fused.launch_count; shipped_fused.update(1.0); assert shipped_fused.launch_count - a == 2
     b = shipped_literal.launch_count; shipped_literal.update(1.0); assert shipped_literal.launch_count - b == 8
