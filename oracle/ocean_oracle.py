@@ -12,10 +12,12 @@ Reference files restated (relative to /root/reference): shader/propagate.comp:42
 shader/fft_row.comp:25-63, shader/fft_col.comp:44-63, shader/correction.comp:24-35,
 src/render.rs:1122-1287.
 
-PARITY UNPINNED: the reference holds no golden vectors / tests for this path; the
-oracle is pinned by the shader sources, the shipped SPIR-V and the reference-owned
-inputs only. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs may import this module.
+PARITY PINNED BY EXECUTION OF THE REFERENCE'S OWN SHADER BINARIES: the reference holds no
+golden vectors / tests for this path, so oracle/spv_exec.py interprets the SPIR-V modules the
+reference ships and dispatches (shader/spv/*.spv) on the reference-owned inputs; the resulting
+fixtures (tests/golden/spv_512.npz, generator tests/golden/make_spv_golden.py) agree with this
+restatement to <= 6e-7 (tests/test_spv_pin.py; bar 1e-5). Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs may import this module.
 """
 from __future__ import annotations
 
@@ -209,6 +211,33 @@ def normal_map_np(disp):
     c = np.cross(na, nb)
     c /= np.linalg.norm(c, axis=-1, keepdims=True)
     return np.concatenate([c, np.zeros(d.shape + (1,))], -1)
+
+
+def sample_linear_tile_np(disp, u, v):
+    """Vulkan linear filtering with REPEAT addressing (the reference's sampler: Filter::Linear,
+    WrapMode::Tile, src/render.rs:397-398) of a [H, W, C] map at normalised coordinates (u, v)."""
+    d = np.asarray(disp, np.float64)
+    h, w = d.shape[:2]
+    x = np.asarray(u, np.float64) * w - 0.5
+    y = np.asarray(v, np.float64) * h - 0.5
+    i0, j0 = np.floor(x), np.floor(y)
+    a, b = (x - i0)[..., None], (y - j0)[..., None]
+    i0, j0 = i0.astype(np.int64), j0.astype(np.int64)
+    i1, j1 = (i0 + 1) % w, (j0 + 1) % h
+    i0, j0 = i0 % w, j0 % h
+    return (d[j0, i0] * (1 - a) + d[j0, i1] * a) * (1 - b) + (d[j1, i0] * (1 - a) + d[j1, i1] * a) * b
+
+
+def displace_grid_np(disp, grid, offset=(0.0, 0.0)):
+    """shader/ocean.vert:21-25,29 for the reference's vertex grid (src/render.rs:498-506: a_Pos = (x, 0, z),
+    a_Uv = (x, z) / (grid - 1) computed in f32): p_PosWorld = a_Pos + (d.x/3.5, d.y/3, d.z/3.5) + (off.x, 0, off.y)
+    with d = texture(displacement_map, a_Uv). -> [grid, grid, 3] float64."""
+    g = np.arange(grid, dtype=np.float32)
+    uvs = (g / np.float32(grid - 1)).astype(np.float64)
+    x, z = np.meshgrid(g.astype(np.float64), g.astype(np.float64), indexing="xy")
+    u, v = np.meshgrid(uvs, uvs, indexing="xy")
+    d = sample_linear_tile_np(disp, u, v)
+    return np.stack([x + d[..., 0] / 3.5 + offset[0], d[..., 1] / 3.0, z + d[..., 2] / 3.5 + offset[1]], -1)
 
 
 def stockham_line_np(x: np.ndarray, pi=float(PI32)) -> np.ndarray:
