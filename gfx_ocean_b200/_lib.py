@@ -11,9 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # OCEAN_B200_LIB selects an alternative build of the same library (A/B experiments, scripts/ab_build.sh)
 LIB_PATH = os.environ.get("OCEAN_B200_LIB") or os.path.join(HERE, "libocean_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_IO, ERR_NOT_READY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 PIPELINE_FUSED, PIPELINE_LITERAL = 0, 1
+FLAG_KEEP_SPECTRA, FLAG_DOUBLE_BUFFER_OUTPUT = 1, 2
 
 
 class PropagateLocals(C.Structure):
@@ -30,6 +31,10 @@ class OceanConfig(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("cuda_device", C.c_int32), ("resolution", C.c_uint32),
                 ("domain_size", C.c_float), ("n_tiles", C.c_uint32), ("pipeline", C.c_uint32),
                 ("stream", C.c_void_p), ("flags", C.c_uint32)]
+
+
+class SpectrumParams(C.Structure):
+    _fields_ = [("amplitude", C.c_float), ("wind_speed", C.c_float), ("gravity", C.c_float), ("depth", C.c_float)]
 
 
 class OceanError(RuntimeError):
@@ -51,10 +56,20 @@ SIGNATURES = {
     "ocean_update": (C.c_int, [_P, _F]),
     "ocean_update_tiles": (C.c_int, [_P, _F, _U32, _U32]),
     "ocean_update_sequence": (C.c_int, [_P, _F, _F, _U32]),
+    "ocean_update_graph": (C.c_int, [_P, _F, _U32, _U32]),
     "ocean_output_device": (C.c_int, [_P, _U32, C.POINTER(_P)]),
     "ocean_download": (C.c_int, [_P, _U32, _P]),
     "ocean_download_async": (C.c_int, [_P, _U32, _P]),
+    "ocean_download_all_async": (C.c_int, [_P, _P]),
+    "ocean_download_fence": (C.c_int, [_P, _U32]),
     "ocean_sync": (C.c_int, [_P]),
+    "ocean_set_output_device": (C.c_int, [_P, _U32, _P, C.c_size_t]),
+    "ocean_update_sequence_checksums": (C.c_int, [_P, _F, _F, _U32, _P]),
+    "ocean_output_checksums": (C.c_int, [_P, _P]),
+    "ocean_displace_grid": (C.c_int, [_P, _U32, _U32, _F, _F, _P]),
+    "ocean_displace_grid_device": (C.c_int, [_P, _U32, _U32, _F, _F, _P]),
+    "ocean_generate_spectrum": (C.c_int, [_P, _U32, _U64, _U32, C.POINTER(SpectrumParams), _P]),
+    "ocean_get_spectrum": (C.c_int, [_P, _U32, _P, _P]),
     "ocean_debug_spectra": (C.c_int, [_P, _U32, _P, _P, _P]),
     "ocean_compute_normals": (C.c_int, [_P, _U32, _U32]),
     "ocean_normals_device": (C.c_int, [_P, _U32, C.POINTER(_P)]),

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libocean_b200.so")
-SOURCES = ["ocean_api.cu", "kernels_literal.cu", "kernels_fused.cu"]
+SOURCES = ["ocean_api.cu", "kernels_literal.cu", "kernels_consumer.cu", "kernels_fused.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -38,12 +38,21 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    extra = os.environ.get("OCEAN_NVCC_EXTRA", "").split()      # extra -D flags for A/B builds (scripts/ab_build.sh)
-    if not force and not extra and not _stale():
-        return LIB
+def build(force: bool = False, verbose: bool = False, variant: str | None = None, extra: list[str] | None = None) -> str:
+    """Build the default library, or -- with `variant` -- an A/B build with extra nvcc flags into
+    gfx_ocean_b200/variants/libocean_b200.<variant>.so (separate object directory; the default library is
+    never touched, so later tests and benches cannot silently run an experimental configuration)."""
+    extra = list(extra or [])
+    if variant is None:
+        if extra:
+            raise ValueError("extra flags need a variant name: the default library is always the default configuration")
+        if not force and not _stale():
+            return LIB
+        out, bdir = LIB, os.path.join(HERE, "build")
+    else:
+        os.makedirs(os.path.join(HERE, "variants"), exist_ok=True)
+        out, bdir = os.path.join(HERE, "variants", f"libocean_b200.{variant}.so"), os.path.join(HERE, "build", variant)
     objs = []
-    bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
@@ -56,13 +65,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(obj + ".ptxas.log", "w") as f:
             f.write(r.stdout)
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
         print(r.stdout)
         raise RuntimeError("link failed")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m gfx_ocean_b200.build [--force] [-v] [--variant NAME -DFLAG=.. ...]
+    argv = sys.argv[1:]
+    variant = argv[argv.index("--variant") + 1] if "--variant" in argv else None
+    extra = [a for a in argv if a.startswith("-D") or a.startswith("-maxrregcount")]
+    print(build(force="--force" in argv, verbose="-v" in argv, variant=variant, extra=extra))

@@ -295,9 +295,8 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// k_cols: persistent, bulk-copy fed, warp-specialised
-// ------------------------------------------------------------------------------------------
+
+// mbarrier / bulk-copy (TMA) / named-barrier wrappers shared by k_rows_p and k_cols
 namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
@@ -354,6 +353,329 @@ template <int ID, int COUNT>
 __device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
 }  // namespace ptx
 
+// ------------------------------------------------------------------------------------------
+// k_rows_p: persistent, bulk-copy fed k_rows with the Hermitian fold done at the source
+// ------------------------------------------------------------------------------------------
+// One CTA per SM: GROUPS independent groups of 3*PAIRS*T threads plus (SLOTS > 0) one producer warp. A group takes
+// "units" (PAIRS consecutive row pairs of one tile) from the CTA's contiguous share of the launch through a
+// shared-memory ticket. Per unit:
+//   producer one elected thread bulk-copies (cp.async.bulk + mbarrier complete_tx) the unit's raw rows -- per row pair
+//            four rows of h0 and two of omega, 40 KB at N = 1024 -- into a ring of SLOTS unit slots, running ahead of
+//            the groups: phase A never waits on DRAM and no register stages a global load.
+//   phase A  all threads of the group walk x: the thread that owns x evaluates propagate.comp for BOTH points a
+//            fold needs -- (x, y) and (-x, N-y) -- and writes the three folded sequences (row y of P, row N-y of
+//            P, row y of h_S) straight into the lines the transforms run on. Every spectrum value and unit wave
+//            vector is computed once and never parked in shared memory: per row pair the shared-memory traffic
+//            of the fold is 24 KB written + 24 KB read, against 32 KB written + 96 KB read when the propagated
+//            rows were staged as (h, khat) records and folded by each of the three line warps (round 1; its ncu
+//            profile had the L1/shared pipe, not DRAM, as the busiest unit).
+//   phase B  one line per T threads: pass 1 in registers, twiddle, IN-PLACE exchange through the same line
+//            (a thread writes back exactly the padded slots it read), pass 2 (and 3), strip-major stores.
+// A thread executes griddepcontrol.wait once, before its first store to the intermediate, so the write-after-read
+// hazard against the previous frame's k_cols is closed per storing thread (no assumption on block dispatch order).
+// The inputs h0 / omega are never written by a frame kernel, so the producer's copies need no such wait.
+#ifndef OCEAN_ROWS_UNROLL
+#define OCEAN_ROWS_UNROLL 4
+#endif
+template <int N, int P, int PAIRS, int C, int GROUPS, int SLOTS>
+struct RowsCfg {
+    using Line = LineCfg<N, P>;
+    static constexpr int T = Line::T;
+    static constexpr int LINES = 3 * PAIRS;               // lines per group
+    static constexpr int GT = LINES * T;                  // threads per group
+    static constexpr int NTHREADS = GROUPS * GT + (SLOTS > 0 ? 32 : 0);
+    static constexpr int UPT = N / 2 / PAIRS;             // units per tile
+    static constexpr size_t GROUP_SMEM = sizeof(float2) * LINES * Line::LINE;
+    static constexpr size_t LINES_SMEM = GROUPS * GROUP_SMEM;
+    // raw rows of one row pair: h0 rows [F0][P0][F1][P1], omega rows [W0][W1]
+    static constexpr uint32_t PAIR_RAW = 4 * N * sizeof(float2) + 2 * N * sizeof(float);
+    static constexpr uint32_t SLOT_BYTES = PAIRS * PAIR_RAW;
+    static constexpr size_t SMEM = LINES_SMEM + size_t(SLOTS) * SLOT_BYTES + (SLOTS > 0 ? 2 * SLOTS * sizeof(uint64_t) : 0);
+    static_assert(GT % 32 == 0 && GROUPS >= 1 && GROUPS <= 15, "groups synchronise on named barriers 1..GROUPS");
+    static_assert(LINES_SMEM % 16 == 0 && PAIR_RAW % 16 == 0, "bulk copies need 16-byte granules");
+};
+
+// propagate.comp:42-72 for one grid point, as the record the folds consume: (h.re, h.im, khat.x, khat.z)
+__device__ __forceinline__ float4 propagate_record(float2 h0, float2 h0_rev, float omega, float kx, float ky, float time)
+{
+    const float2 h = propagate_point_fast(h0, h0_rev, omega, time);
+    const float2 k = unit_wave_vector_fast(kx, ky);
+    return make_float4(h.x, h.y, k.x, k.y);
+}
+
+// rows of h0 / omega a row pair needs (in slot order F0 P0 F1 P1 | W0 W1). h0's partner is the REVERSED array
+// (propagate.comp:48): the partner of (x, r) is (N-1-x, N-1-r).
+//   pair j > 0: A = (x, j) and B = (-x, N-j):  F0 = j, P0 = N-1-j, F1 = N-j, P1 = j-1;      W0 = j, W1 = N-j
+//   pair 0    : rows 0 and N/2 are their own partners: F0 = 0, P0 = N-1, F1 = N/2, P1 = N/2-1;  W0 = 0, W1 = N/2
+template <int N>
+__device__ __forceinline__ void pair_rows(uint32_t j, uint32_t (&h)[4], uint32_t (&w)[2])
+{
+    if (j) { h[0] = j; h[1] = N - 1 - j; h[2] = N - j; h[3] = j - 1; w[0] = j; w[1] = N - j; }
+    else { h[0] = 0; h[1] = N - 1; h[2] = N / 2; h[3] = N / 2 - 1; w[0] = 0; w[1] = N / 2; }
+}
+
+// Phase A for one row pair. F0 P0 F1 P1 W0 W1: the six rows (global memory with read-only loads, or the raw slot in
+// shared memory). Writes the three folded sequences into L0 L1 L2 at pad(x).
+template <class Cfg, bool GLOBAL_SRC, class Ld2, class Ld1>
+__device__ __forceinline__ void fold_pair(uint32_t jp, const float2* F0, const float2* P0, const float2* F1, const float2* P1,
+                                          const float* W0, const float* W1, const float* __restrict__ kx_g, float time,
+                                          float2* L0, float2* L1, float2* L2, int gt, int GT, Ld2 ld2, Ld1 ld1)
+{
+    constexpr int N = Cfg::N;
+    const int ITER = (N + GT - 1) / GT;
+    if (jp != 0) {
+        // A = (x, y) from F0 / P0 / W0, B = ((N-x)%N, N-y) from F1 / P1 / W1 (its partner sits at column (x-1)%N)
+        const float kya = __ldg(kx_g + jp), kyb = __ldg(kx_g + (N - jp));
+        constexpr int U = GLOBAL_SRC ? OCEAN_ROWS_UNROLL : 2;          // x values in flight per thread
+#pragma unroll 1
+        for (int u0 = 0; u0 < ITER; u0 += U) {
+            float2 a0[U], a1[U], b0[U], b1[U];
+            float oa[U], ob[U], ka[U], kb[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t x = gt + (u0 + u) * GT;
+                if (x < N) {
+                    const uint32_t xm = (N - x) & (N - 1), xp = (x - 1) & (N - 1);
+                    a0[u] = ld2(F0 + x);
+                    a1[u] = ld2(P0 + (N - 1 - x));
+                    oa[u] = ld1(W0 + x);
+                    b0[u] = ld2(F1 + xm);
+                    b1[u] = ld2(P1 + xp);
+                    ob[u] = ld1(W1 + xm);
+                    ka[u] = __ldg(kx_g + x);
+                    kb[u] = __ldg(kx_g + xm);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t x = gt + (u0 + u) * GT;
+                if (x < N) {
+                    const float4 A = propagate_record(a0[u], a1[u], oa[u], ka[u], kya, time);
+                    const float4 B = propagate_record(b0[u], b1[u], ob[u], kb[u], kyb, time);
+                    const float2 qa = rot_mul(A), qac = rot_mul_conj(A), qb = rot_mul(B), qbc = rot_mul_conj(B);
+                    const int s = Cfg::pad(x);
+                    L0[s] = make_float2(qa.x - qbc.x, qa.y - qbc.y);      // row y of P_S
+                    L1[s] = make_float2(qb.x - qac.x, qb.y - qac.y);      // row N-y of P_S, mirrored sequence
+                    L2[s] = make_float2(A.x + B.x, A.y - B.y);            // row y of h_S
+                }
+            }
+        }
+    } else {
+        // rows 0 and N/2: P_S(x; r) from (x, r) and (-x, r) in natural order, and h_S(x, 0) + i h_S(x, N/2) (both row
+        // transforms are real, so they share one complex transform)
+#pragma unroll 1
+        for (uint32_t x = gt; x < N; x += GT) {
+            const uint32_t xm = (N - x) & (N - 1), xp = (x - 1) & (N - 1);
+            const float kxa = __ldg(kx_g + x), kxb = __ldg(kx_g + xm);
+            float2 hs[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float ky = __ldg(kx_g + (i ? N / 2 : 0));
+                const float2* fr = i ? F1 : F0;
+                const float2* pr = i ? P1 : P0;
+                const float* wr = i ? W1 : W0;
+                const float4 A = propagate_record(ld2(fr + x), ld2(pr + (N - 1 - x)), ld1(wr + x), kxa, ky, time);
+                const float4 B = propagate_record(ld2(fr + xm), ld2(pr + xp), ld1(wr + xm), kxb, ky, time);
+                const float2 qa = rot_mul(A), qbc = rot_mul_conj(B);
+                (i ? L1 : L0)[Cfg::pad(x)] = make_float2(qa.x - qbc.x, qa.y - qbc.y);
+                hs[i] = make_float2(A.x + B.x, A.y - B.y);
+            }
+            L2[Cfg::pad(x)] = make_float2(hs[0].x - hs[1].y, hs[0].y + hs[1].x);
+        }
+    }
+}
+
+// (ptxas sizes registers for the thread count rounded up to whole groups of four warps: each of the SM's four
+// sub-partitions has its own 16 K-register file, so 15 warps cost what 16 do -- the producer warp is free)
+template <int N, int P, int PAIRS, int C, int GROUPS, int SLOTS>
+__global__ void __launch_bounds__(RowsCfg<N, P, PAIRS, C, GROUPS, SLOTS>::NTHREADS, 1)
+k_rows_p(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, const float2* __restrict__ tw_g,
+         const float* __restrict__ kx_g, float2* __restrict__ gp_all, float2* __restrict__ gh_all, float time,
+         uint32_t first_tile, uint32_t n_units)
+{
+    using RC = RowsCfg<N, P, PAIRS, C, GROUPS, SLOTS>;
+    using Cfg = typename RC::Line;
+    using IL = Inter<N, C, Cfg::GS>;
+    constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2, GT = RC::GT;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_next;
+    __shared__ uint32_t s_unit[2][GROUPS];   // the group's next unit, double-buffered by iteration parity
+    __shared__ uint32_t s_done[SLOTS > 0 ? SLOTS : 1];   // units whose phase A has drained each raw slot (monotonic)
+    unsigned char* raw_base = smem_raw + RC::LINES_SMEM;
+    uint64_t* full = reinterpret_cast<uint64_t*>(raw_base + size_t(SLOTS) * RC::SLOT_BYTES);   // [SLOTS] raw rows landed (tx bytes)
+    uint64_t* empty = full + SLOTS;                                                             // [SLOTS] phase A done (GT arrivals)
+
+    const int tid = threadIdx.x;
+    pdl_launch_dependents();
+    const uint32_t u_begin = uint32_t(uint64_t(blockIdx.x) * n_units / gridDim.x);
+    const uint32_t u_end = uint32_t(uint64_t(blockIdx.x + 1) * n_units / gridDim.x);
+    if (tid == 0) {
+        s_next = u_begin + GROUPS;
+        if constexpr (SLOTS > 0) {
+            for (int i = 0; i < SLOTS; ++i) {
+                s_done[i] = 0;
+                ptx::mbar_init(full + i, 1);
+                ptx::mbar_init(empty + i, GT);
+            }
+            ptx::fence_mbar_init();
+        }
+    }
+    __syncthreads();
+
+    if constexpr (SLOTS > 0) {
+        if (tid >= GROUPS * GT) {
+            // ================= producer warp =================
+            if ((tid & 31) == 0) {
+                for (uint32_t k = 0; u_begin + k < u_end; ++k) {
+                    const uint32_t slot = k % SLOTS, unit = u_begin + k;
+                    const uint32_t tl = unit / RC::UPT, bx = unit % RC::UPT;
+                    const float2* h0 = h0_all + size_t(first_tile + tl) * N * N;
+                    const float* omega = omega_all + size_t(first_tile + tl) * N * N;
+                    if (k >= SLOTS) {
+                        ptx::mbar_wait_backoff(empty + slot, ((k / SLOTS) - 1) & 1);    // the group that had this slot is done reading
+                        ptx::fence_proxy_async();
+                    }
+                    ptx::mbar_arrive_expect_tx(full + slot, RC::SLOT_BYTES);
+                    unsigned char* dst = raw_base + size_t(slot) * RC::SLOT_BYTES;
+#pragma unroll 1
+                    for (int p = 0; p < PAIRS; ++p) {
+                        uint32_t hr[4], wr[2];
+                        pair_rows<N>(bx * PAIRS + p, hr, wr);
+                        for (int i = 0; i < 4; ++i, dst += N * sizeof(float2))
+                            ptx::bulk_g2s(dst, h0 + size_t(hr[i]) * N, N * sizeof(float2), full + slot);
+                        for (int i = 0; i < 2; ++i, dst += N * sizeof(float))
+                            ptx::bulk_g2s(dst, omega + size_t(wr[i]) * N, N * sizeof(float), full + slot);
+                    }
+                }
+            }
+            return;
+        }
+    }
+
+    const int g = tid / GT, gt = tid % GT;
+    float2* lines = reinterpret_cast<float2*>(smem_raw) + size_t(g) * RC::LINES * Cfg::LINE;
+    auto group_bar = [&] { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GT) : "memory"); };
+    bool waited = false;
+
+    // phase B roles
+    const int f = gt / T;                 // line in the group
+    const int pair = f / 3, seq = f % 3;
+    const int k2 = gt % T;
+    float2* line = lines + f * Cfg::LINE;
+
+    uint32_t par = 0;
+#pragma unroll 1
+    for (uint32_t unit = u_begin + g; unit < u_end; par ^= 1u) {
+        const uint32_t tl = unit / RC::UPT, bx = unit % RC::UPT;
+
+        // ---- phase A: propagate + fold -> lines
+        if constexpr (SLOTS > 0) {
+            // The unit's slot is shared with the units SLOTS, 2 SLOTS, ... before it, which other groups consume. A
+            // phase-parity wait alone cannot tell "my rows landed" from "the rows of two occupants ago landed", so
+            // first wait on a monotonic count until every earlier occupant has drained the slot; from then on the
+            // barrier is either pending on this unit's copy or completed by it.
+            const uint32_t k = unit - u_begin, slot = k % SLOTS, occ = k / SLOTS;
+            while (*reinterpret_cast<volatile uint32_t*>(&s_done[slot]) < occ) __nanosleep(32);
+            ptx::mbar_wait(full + slot, occ & 1);
+            const unsigned char* src = raw_base + size_t(slot) * RC::SLOT_BYTES;
+#pragma unroll 1
+            for (int p = 0; p < PAIRS; ++p, src += RC::PAIR_RAW) {
+                const float2* R = reinterpret_cast<const float2*>(src);
+                const float* W = reinterpret_cast<const float*>(src + 4 * N * sizeof(float2));
+                float2* L0 = lines + (3 * p) * Cfg::LINE;
+                fold_pair<Cfg, false>(bx * PAIRS + p, R, R + N, R + 2 * N, R + 3 * N, W, W + N, kx_g, time, L0, L0 + Cfg::LINE,
+                                      L0 + 2 * Cfg::LINE, gt, GT, [](const float2* q) { return *q; }, [](const float* q) { return *q; });
+            }
+            ptx::mbar_arrive(empty + slot);       // this thread's reads of the slot are done
+        } else {
+            const float2* __restrict__ h0 = h0_all + size_t(first_tile + tl) * N * N;
+            const float* __restrict__ omega = omega_all + size_t(first_tile + tl) * N * N;
+#pragma unroll 1
+            for (int p = 0; p < PAIRS; ++p) {
+                uint32_t hr[4], wr[2];
+                pair_rows<N>(bx * PAIRS + p, hr, wr);
+                float2* L0 = lines + (3 * p) * Cfg::LINE;
+                fold_pair<Cfg, true>(bx * PAIRS + p, h0 + size_t(hr[0]) * N, h0 + size_t(hr[1]) * N, h0 + size_t(hr[2]) * N,
+                                     h0 + size_t(hr[3]) * N, omega + size_t(wr[0]) * N, omega + size_t(wr[1]) * N, kx_g, time, L0,
+                                     L0 + Cfg::LINE, L0 + 2 * Cfg::LINE, gt, GT, [](const float2* q) { return __ldg(q); },
+                                     [](const float* q) { return __ldg(q); });
+            }
+        }
+        // Next unit of this group, read by every thread after the unit's last barrier. Two slots: a warp that is slow
+        // to read slot `par` after that barrier cannot be overtaken by the write of the next iteration (other slot);
+        // the write after that one is two barriers away. (With one slot a starved warp read the following ticket
+        // and a row went missing -- found by compute-sanitizer racecheck, seen as sporadic errors in multi-tile runs.)
+        if (gt == 0) s_unit[par][g] = atomicAdd(&s_next, 1u);
+        group_bar();
+        if constexpr (SLOTS > 0) {
+            if (gt == 0) *reinterpret_cast<volatile uint32_t*>(&s_done[(unit - u_begin) % SLOTS]) = (unit - u_begin) / SLOTS + 1;
+        }
+
+        // ---- phase B: one line transform per T threads
+        const uint32_t j = bx * PAIRS + pair;
+        const bool self_paired = (j == 0);
+        float2 v[R1];
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) v[k1] = line[Cfg::pad(k1 * T + k2)];
+        RegFft<R1>::run(v);
+#pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1)          // in place: the slots this thread just read
+            line[Cfg::pad(n1 * T + k2)] = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * T + k2));
+        if constexpr (T <= 32) __syncwarp(); else group_bar();
+        if (!waited) {                       // the previous frame's k_cols may still be reading the intermediate
+            pdl_wait_prior_grid();
+            waited = true;
+        }
+
+        // Destination row in the strip-major intermediate. Thread n1 owns columns n = n1 + R1 n2: strip n / C and
+        // in-strip column n % C advance by a constant per n2 (R1 is a multiple of C), also for the mirrored
+        // sequence, whose column (N - n) mod N runs backwards; only n = 0 maps to itself there.
+        static_assert(R1 % C == 0, "pass-1 radix must cover whole strips");
+        float2* __restrict__ gp = gp_all + size_t(tl) * IL::P_TILE;
+        float2* __restrict__ gh = gh_all + size_t(tl) * IL::H_TILE;
+        float2* dst;
+        bool mirrored = false;
+        if (seq == 0) dst = gp + IL::row_off(j);
+        else if (seq == 1) { dst = gp + IL::row_off(self_paired ? N / 2 : N - j); mirrored = !self_paired; }
+        else dst = gh + IL::row_off(j);
+        const long strip_stride = seq == 2 ? IL::H_STRIP : IL::P_STRIP;
+        if constexpr (Cfg::R3 > 1) {
+            line_passes_23<Cfg>(line, k2, tw_g + N, [&] { group_bar(); }, [&](int n, float2 val) {
+                const uint32_t col = mirrored ? ((N - n) & (N - 1)) : n;
+                dst[long(col / C) * strip_stride + col % C] = val;
+            });
+        } else {
+            const long step = (mirrored ? -long(R1 / C) : long(R1 / C)) * strip_stride;
+#pragma unroll
+            for (int i = 0; i < Cfg::SUB2; ++i) {
+                const int n1 = k2 + R2 * i;
+                float2 u[R2];
+#pragma unroll
+                for (int k = 0; k < R2; ++k) u[k] = line[Cfg::pad(n1 * R2 + k)];
+                RegFft<R2>::run(u);
+                const uint32_t col0 = mirrored ? ((N - n1) & (N - 1)) : n1;          // column of n2 = 0
+                float2* q = dst + long(col0 / C) * strip_stride + col0 % C;
+                if (mirrored && n1 == 0) {
+                    q[0] = u[0];                                                       // n = 0 -> column 0
+                    q += long(N / C) * strip_stride;                                   // n = R1 n2 -> column N - R1 n2
+#pragma unroll
+                    for (int n2 = 1; n2 < R2; ++n2) q[n2 * step] = u[n2];
+                } else {
+#pragma unroll
+                    for (int n2 = 0; n2 < R2; ++n2) q[n2 * step] = u[n2];
+                }
+            }
+        }
+        group_bar();                          // lines are free for the next unit's phase A
+        unit = s_unit[par][g];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_cols: persistent, bulk-copy fed, warp-specialised
+// ------------------------------------------------------------------------------------------
+
 template <int N, int P, int C>
 struct ColsCfg {
     using Line = LineCfg<N, P>;
@@ -380,10 +702,12 @@ struct ColsCfg {
 //                   out(x, y) = (dx, height, dz, 0) * sign / 2  (correction.comp:29-34)
 // GP is double-buffered so the next strip's copy overlaps this strip's transforms and stores; HR lives in
 // the GP buffer the packed warps have just drained into registers, so the two roles only meet once per item.
-template <int N, int P, int C>
+// GENERAL = false is the product build (dense rows of N texels); GENERAL = true honours a per-tile row pitch and
+// can accumulate a checksum of what it stores (tests: PDL on/off and GPU-count determinism).
+template <int N, int P, int C, bool GENERAL>
 __global__ void __launch_bounds__(ColsCfg<N, P, C>::NTHREADS, 1)
 k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, const float2* __restrict__ tw_g,
-       float4* __restrict__ out_all, uint32_t first_tile, uint32_t n_items)
+       const OutDesc* __restrict__ out_tab, uint32_t first_tile, uint32_t n_items, unsigned long long* __restrict__ checksums)
 {
     using CC = ColsCfg<N, P, C>;
     using Cfg = typename CC::Line;
@@ -553,7 +877,18 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
             for (int n1 = 0; n1 < R1; ++n1)
                 col[n1 * K1_STRIDE] = n1 == 0 ? v[0] : cmul_tw(v[n1], TW[n1 * T + k2]);
             ptx::named_bar_sync<1, NTP>();
-            float4* __restrict__ out = out_all + size_t(first_tile + tl) * N * N + n0 + c;
+            const OutDesc od = out_tab[first_tile + tl];
+            float4* __restrict__ out = od.base + n0 + c;
+            const size_t pitch = GENERAL ? size_t(od.pitch) : size_t(N);
+            unsigned long long csum = 0;
+            auto emit = [&](uint32_t m, float dx, float hh, float dz) {
+                // correction.comp:29 sign, times the 1/2 of the Hermitian fold
+                const float sg = ((n0 + c + m) & 1u) ? 0.5f : -0.5f;
+                const float4 t = make_float4(dx * sg, hh * sg, dz * sg, 0.0f);
+                __stcs(out + size_t(m) * pitch, t);
+                if constexpr (GENERAL)
+                    csum += (unsigned long long)__float_as_uint(t.x) + __float_as_uint(t.y) * 3ull + __float_as_uint(t.z) * 5ull;
+            };
             const float* HR = reinterpret_cast<const float*>(PB);
             if constexpr (R3 == 1) {
                 float2 u[Cfg::SUB2][R2];
@@ -573,9 +908,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
 #pragma unroll
                     for (int n2 = 0; n2 < R2; ++n2) {
                         const uint32_t m = n1 + R1 * n2;
-                        // correction.comp:29 sign, times the 1/2 of the Hermitian fold
-                        const float sg = ((n0 + c + m) & 1u) ? 0.5f : -0.5f;
-                        __stcs(out + size_t(m) * N, make_float4(u[i][n2].x * sg, HR[m * C + c] * sg, u[i][n2].y * sg, 0.0f));
+                        emit(m, u[i][n2].x, HR[m * C + c], u[i][n2].y);
                     }
                 }
             } else {
@@ -609,13 +942,19 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
 #pragma unroll
                     for (int n3 = 0; n3 < R3; ++n3) {
                         const uint32_t m = n1 + R1 * n2 + R1 * R2 * n3;
-                        const float sg = ((n0 + c + m) & 1u) ? 0.5f : -0.5f;
-                        __stcs(out + size_t(m) * N, make_float4(w[i][n3].x * sg, HR[m * C + c] * sg, w[i][n3].y * sg, 0.0f));
+                        emit(m, w[i][n3].x, HR[m * C + c], w[i][n3].y);
                     }
                 }
             }
             ptx::fence_proxy_async();          // generic-proxy accesses to PB[b] precede the next bulk copy into it
             ptx::mbar_arrive(hrFree + b);
+            if constexpr (GENERAL) {
+                if (checksums) {
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+                    if (lane == 0) atomicAdd(checksums + tl, csum);
+                }
+            }
         }
     }
 }
@@ -629,28 +968,34 @@ struct FusedPlan {
     int num_sms = 0;
     int cols_blocks_per_sm = 1;  // persistent k_cols blocks resident per SM
     int rows_blocks_per_sm = 1;  // k_rows blocks resident per SM (occupancy)
-    int pdl_mode = -1;           // programmatic dependent launch: -1 auto (small grids), 0 off, 1 on (env OCEAN_B200_PDL)
+    int pdl_mode = -1;           // programmatic dependent launch: -1 auto, 0 off, 1 on (env OCEAN_B200_PDL)
+    int rows_legacy = 0;         // 1: round-1 k_rows (one block per row pair) for A/B runs (env OCEAN_B200_ROWS=legacy)
     float2* d_tw = nullptr;      // [R1][R2] inter-pass twiddles
     float* d_kx = nullptr;       // [N] wave numbers, propagate.comp:45-46,50-53
     float2* d_gp = nullptr;      // [tiles] strip-major packed (dx, dz) row-pass output
     float2* d_gh = nullptr;      // [tiles] strip-major height row-pass output (N/2 rows)
 };
 
-template <int N, int P, int PAIRS, int C, int MINB>
+template <int N, int P, int PAIRS, int C, int MINB, int PPAIRS, int GROUPS, int SLOTS>
 struct Launch {
     using Cfg = LineCfg<N, P>;
     using CC = ColsCfg<N, P, C>;
     using IL = typename CC::IL;
+    using RC = RowsCfg<N, P, PPAIRS, C, GROUPS, SLOTS>;
     static constexpr size_t smem_rows = sizeof(float4) * 2 * PAIRS * (N + 1);
 
     static cudaError_t prepare(FusedPlan* p)
     {
         cudaError_t e = cudaFuncSetAttribute(k_rows<N, P, PAIRS, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_rows));
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_cols<N, P, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(CC::SMEM));
+        e = cudaFuncSetAttribute(k_rows_p<N, P, PPAIRS, C, GROUPS, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(RC::SMEM));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_cols<N, P, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(CC::SMEM));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_cols<N, P, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(CC::SMEM));
         if (e != cudaSuccess) return e;
         int per_sm = 1;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cols<N, P, C>, CC::NTHREADS, CC::SMEM);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cols<N, P, C, false>, CC::NTHREADS, CC::SMEM);
         p->cols_blocks_per_sm = per_sm < 1 ? 1 : per_sm;
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rows<N, P, PAIRS, C, MINB>, 3 * PAIRS * Cfg::T, smem_rows);
@@ -660,28 +1005,40 @@ struct Launch {
     static size_t gp_floats2_per_tile() { return IL::P_TILE; }
     static size_t gh_floats2_per_tile() { return IL::H_TILE; }
 
-    static cudaError_t run(FusedPlan* p, const float2* h0, const float* omega, float4* out, float time,
-                           uint32_t first_tile, uint32_t count, cudaStream_t s, cudaEvent_t* ev)
+    static cudaError_t run(FusedPlan* p, const float2* h0, const float* omega, const OutDesc* out, float time,
+                           uint32_t first_tile, uint32_t count, cudaStream_t s, cudaEvent_t* ev, bool general,
+                           unsigned long long* checksums)
     {
         if (ev) cudaEventRecord(ev[0], s);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        // measured on B200 (N=1024): PDL gains 21% / 7% at 1 / 4 tiles per launch (it hides ramp and tail) and
-        // loses 1.5-3.5% at 8-16 tiles, so it is used while the row grid is below four waves
-        const bool pdl = p->pdl_mode == 1 || (p->pdl_mode < 0 && (N / 2 / PAIRS) * count < 4u * uint32_t(p->num_sms) * MINB);
-        attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
         cudaLaunchConfig_t cfg{};
         cfg.stream = s;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cfg.gridDim = dim3(N / 2 / PAIRS, count);
-        cfg.blockDim = dim3(3 * PAIRS * Cfg::T);
-        cfg.dynamicSmemBytes = smem_rows;
         const float2* tw = p->d_tw;
         const float* kx = p->d_kx;
         float2 *gp = p->d_gp, *gh = p->d_gh;
-        const uint32_t resident = uint32_t(p->num_sms * p->rows_blocks_per_sm);
-        cudaError_t e = cudaLaunchKernelEx(&cfg, k_rows<N, P, PAIRS, C, MINB>, h0, omega, tw, kx, gp, gh, time, first_tile, resident);
+        cudaError_t e;
+        if (p->rows_legacy) {
+            // measured on B200 (N=1024): PDL gains 21% / 7% at 1 / 4 tiles per launch (it hides ramp and tail) and
+            // loses 1.5-3.5% at 8-16 tiles, so it is used while the row grid is below four waves
+            const bool pdl = p->pdl_mode == 1 || (p->pdl_mode < 0 && (N / 2 / PAIRS) * count < 4u * uint32_t(p->num_sms) * MINB);
+            attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+            cfg.gridDim = dim3(N / 2 / PAIRS, count);
+            cfg.blockDim = dim3(3 * PAIRS * Cfg::T);
+            cfg.dynamicSmemBytes = smem_rows;
+            const uint32_t resident = uint32_t(p->num_sms * p->rows_blocks_per_sm);
+            e = cudaLaunchKernelEx(&cfg, k_rows<N, P, PAIRS, C, MINB>, h0, omega, tw, kx, gp, gh, time, first_tile, resident);
+        } else {
+            // persistent rows: every storing thread waits on the prior grid itself, so PDL is safe at any size
+            attr[0].val.programmaticStreamSerializationAllowed = p->pdl_mode == 0 ? 0 : 1;
+            const uint32_t units = count * uint32_t(RC::UPT);
+            cfg.gridDim = dim3(units < uint32_t(p->num_sms) ? units : uint32_t(p->num_sms));
+            cfg.blockDim = dim3(RC::NTHREADS);
+            cfg.dynamicSmemBytes = RC::SMEM;
+            e = cudaLaunchKernelEx(&cfg, k_rows_p<N, P, PPAIRS, C, GROUPS, SLOTS>, h0, omega, tw, kx, gp, gh, time, first_tile, units);
+        }
         if (e != cudaSuccess) return e;
         if (ev) cudaEventRecord(ev[1], s);
         const uint32_t items = count * (N / C);
@@ -690,15 +1047,17 @@ struct Launch {
         cfg.blockDim = dim3(CC::NTHREADS);
         cfg.dynamicSmemBytes = CC::SMEM;
         const float2 *cgp = p->d_gp, *cgh = p->d_gh;
-        e = cudaLaunchKernelEx(&cfg, k_cols<N, P, C>, cgp, cgh, tw, out, first_tile, items);
+        e = general ? cudaLaunchKernelEx(&cfg, k_cols<N, P, C, true>, cgp, cgh, tw, out, first_tile, items, checksums)
+                    : cudaLaunchKernelEx(&cfg, k_cols<N, P, C, false>, cgp, cgh, tw, out, first_tile, items, checksums);
         if (ev) cudaEventRecord(ev[2], s);
         return e;
     }
 };
 
-using L64 = Launch<64, 8, 4, 8, 4>;       // small grids: 8 x 8 and 16 x 8 lines, several row pairs per block
-using L128 = Launch<128, 16, 4, 8, 4>;
-using L256 = Launch<256, 16, 2, 8, 4>;
+// Launch<N, P, legacy PAIRS, C, legacy MINB, persistent PAIRS, persistent GROUPS, raw-row ring SLOTS (0: plain loads)>
+using L64 = Launch<64, 8, 4, 8, 4, 4, 4, 4>;       // small grids: 8 x 8 and 16 x 8 lines, several row pairs per unit
+using L128 = Launch<128, 16, 4, 8, 4, 4, 4, 4>;
+using L256 = Launch<256, 16, 2, 8, 4, 2, 5, 4>;
 // N=512 (the reference's own size): one row pair per block (48 threads), 8 blocks/SM at 128 registers measured
 // best of {1,2,4} pairs x {2..8} blocks (283 k frames/s batched, 122 k one tile per update)
 #ifndef OCEAN_ROWS_PAIRS_512
@@ -707,8 +1066,20 @@ using L256 = Launch<256, 16, 2, 8, 4>;
 #ifndef OCEAN_ROWS_MINB_512
 #define OCEAN_ROWS_MINB_512 8
 #endif
-using L512 = Launch<512, 32, OCEAN_ROWS_PAIRS_512, 8, OCEAN_ROWS_MINB_512>;
-using L2048 = Launch<2048, 32, 1, 4, 2>;   // three-pass lines (32 x 32 x 2), strips of 4 columns
+#ifndef OCEAN_ROWS_GROUPS_512
+#define OCEAN_ROWS_GROUPS_512 5
+#endif
+#ifndef OCEAN_ROWS_SLOTS_512
+#define OCEAN_ROWS_SLOTS_512 2
+#endif
+using L512 = Launch<512, 32, OCEAN_ROWS_PAIRS_512, 8, OCEAN_ROWS_MINB_512, 2, OCEAN_ROWS_GROUPS_512, OCEAN_ROWS_SLOTS_512>;
+#ifndef OCEAN_ROWS_GROUPS_2048
+#define OCEAN_ROWS_GROUPS_2048 2
+#endif
+#ifndef OCEAN_ROWS_SLOTS_2048
+#define OCEAN_ROWS_SLOTS_2048 1
+#endif
+using L2048 = Launch<2048, 32, 1, 4, 2, 1, OCEAN_ROWS_GROUPS_2048, OCEAN_ROWS_SLOTS_2048>;   // three-pass lines (32 x 32 x 2), strips of 4 columns
 // k_rows at N=1024: 5 blocks/SM (128 registers, no spills) measured faster than 6 blocks/SM at 96 registers
 // (68 vs 76 us per 8 tiles); overridable for A/B builds (scripts/ab_build.sh)
 #ifndef OCEAN_ROWS_PAIRS_1024
@@ -720,7 +1091,13 @@ using L2048 = Launch<2048, 32, 1, 4, 2>;   // three-pass lines (32 x 32 x 2), st
 #ifndef OCEAN_STRIP_1024
 #define OCEAN_STRIP_1024 8           // 4-column strips (two k_cols blocks per SM) measured 10 % slower
 #endif
-using L1024 = Launch<1024, 32, OCEAN_ROWS_PAIRS_1024, OCEAN_STRIP_1024, OCEAN_ROWS_MINB_1024>;
+#ifndef OCEAN_ROWS_GROUPS_1024
+#define OCEAN_ROWS_GROUPS_1024 5     // 480 threads at <= 128 registers
+#endif
+#ifndef OCEAN_ROWS_SLOTS_1024
+#define OCEAN_ROWS_SLOTS_1024 2      // 2 x 40 KB of raw rows in flight beside the 5 x 25 KB of lines
+#endif
+using L1024 = Launch<1024, 32, OCEAN_ROWS_PAIRS_1024, OCEAN_STRIP_1024, OCEAN_ROWS_MINB_1024, 1, OCEAN_ROWS_GROUPS_1024, OCEAN_ROWS_SLOTS_1024>;
 
 bool fused_supports(uint32_t n) { return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048; }
 
@@ -752,6 +1129,7 @@ cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, flo
     p->n_tiles = n_tiles;
     p->domain_size = domain_size;
     if (const char* v = std::getenv("OCEAN_B200_PDL")) p->pdl_mode = v[0] == '1' ? 1 : (v[0] == '0' ? 0 : -1);
+    if (const char* v = std::getenv("OCEAN_B200_ROWS")) p->rows_legacy = v[0] == 'l' ? 1 : 0;
     cudaError_t e;
     auto bail = [&](cudaError_t err) { fused_plan_destroy(p); return err; };
     if ((e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail(e);
@@ -805,17 +1183,18 @@ void fused_plan_destroy(FusedPlan* p)
     delete p;
 }
 
-cudaError_t fused_enqueue(FusedPlan* p, const float2* h0, const float* omega, float4* out, float time,
-                          uint32_t first_tile, uint32_t count, cudaStream_t s, uint32_t* launches, cudaEvent_t* ev)
+cudaError_t fused_enqueue(FusedPlan* p, const float2* h0, const float* omega, const OutDesc* out, float time,
+                          uint32_t first_tile, uint32_t count, cudaStream_t s, uint32_t* launches, cudaEvent_t* ev,
+                          bool general, unsigned long long* checksums)
 {
     cudaError_t e;
     switch (p->n) {
-        case 64: e = L64::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
-        case 128: e = L128::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
-        case 256: e = L256::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
-        case 512: e = L512::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
-        case 1024: e = L1024::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
-        case 2048: e = L2048::run(p, h0, omega, out, time, first_tile, count, s, ev); break;
+        case 64: e = L64::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
+        case 128: e = L128::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
+        case 256: e = L256::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
+        case 512: e = L512::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
+        case 1024: e = L1024::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
+        case 2048: e = L2048::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
         default: return cudaErrorInvalidValue;
     }
     if (launches) *launches = 2;

@@ -70,45 +70,15 @@ __global__ void k_fft_literal(float2* __restrict__ fft_data, uint32_t n, uint32_
 
 __global__ void __launch_bounds__(256)
 k_correction_literal(const float2* __restrict__ height, const float2* __restrict__ disp_x,
-                     const float2* __restrict__ disp_z, uint32_t n, float4* __restrict__ out)
+                     const float2* __restrict__ disp_z, uint32_t n, float4* __restrict__ out, size_t out_pitch)
 {
     const uint32_t gx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t gy = blockIdx.y * blockDim.y + threadIdx.y;
     if (gx >= n || gy >= n) return;
     const uint32_t index = gx + n * gy;                                  // correction.comp:25
     const float sign_mul = ((gx + gy) % 2u == 0u) ? -1.0f : 1.0f;        // :29
-    out[index] = make_float4(disp_x[index].x * sign_mul, height[index].x * sign_mul,
-                             disp_z[index].x * sign_mul, 0.0f);          // :31-34
-}
-
-// Consumer step: the normal map the fragment shader derives per pixel (shader/ocean.frag:50-66), evaluated
-// once per texel centre. One thread per texel; the four neighbour reads are L2 hits right after k_cols.
-__global__ void __launch_bounds__(256)
-k_normal_map(const float4* __restrict__ disp, float4* __restrict__ nrm, uint32_t n)
-{
-    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= n) return;
-    const float4* __restrict__ d = disp + size_t(blockIdx.z) * n * n;
-    const uint32_t m = n - 1;                                           // Tile wrap (src/render.rs:398), N is a power of two
-    const float x0 = __ldg(&d[((x - 1) & m) + size_t(n) * y].x);        // ocean.frag:56-59, channel .x
-    const float x1 = __ldg(&d[((x + 1) & m) + size_t(n) * y].x);
-    const float z0 = __ldg(&d[x + size_t(n) * ((y - 1) & m)].x);
-    const float z1 = __ldg(&d[x + size_t(n) * ((y + 1) & m)].x);
-    const float diff = 2.0f / float(n);                                 // :52 (dim is hard-coded 512 there)
-    const float height_scale = 180.0f;                                  // :19
-    float nax = -diff, nay = (x1 - x0) / height_scale;                  // :64
-    float nby = (z1 - z0) / height_scale, nbz = diff;                   // :65
-    const float la = sqrtf(nax * nax + nay * nay), lb = sqrtf(nby * nby + nbz * nbz);
-    nax /= la; nay /= la; nby /= lb; nbz /= lb;
-    const float cx = nay * nbz, cy = -nax * nbz, cz = nax * nby;        // :66 cross(na, nb)
-    const float lc = sqrtf(cx * cx + cy * cy + cz * cz);
-    nrm[size_t(blockIdx.z) * n * n + x + size_t(n) * y] = make_float4(cx / lc, cy / lc, cz / lc, 0.0f);
-}
-
-cudaError_t launch_normal_map(const float4* disp, float4* nrm, uint32_t n, uint32_t tiles, cudaStream_t s)
-{
-    k_normal_map<<<dim3((n + 255) / 256, n, tiles), 256, 0, s>>>(disp, nrm, n);
-    return cudaGetLastError();
+    out[gx + out_pitch * gy] = make_float4(disp_x[index].x * sign_mul, height[index].x * sign_mul,
+                                           disp_z[index].x * sign_mul, 0.0f);          // :31-34 (imageStore at (gx, gy))
 }
 
 static uint32_t log2u(uint32_t n) { uint32_t s = 0; while ((1u << s) < n) ++s; return s; }
@@ -136,10 +106,10 @@ cudaError_t launch_fft_row_literal(float2* data, uint32_t n, cudaStream_t s) { r
 cudaError_t launch_fft_col_literal(float2* data, uint32_t n, cudaStream_t s) { return launch_fft<true>(data, n, s); }
 
 cudaError_t launch_correction_literal(const float2* h, const float2* dx, const float2* dz, uint32_t n,
-                                      float4* out, cudaStream_t s)
+                                      float4* out, size_t out_pitch, cudaStream_t s)
 {
     const dim3 block(16, 16), grid((n + 15) / 16, (n + 15) / 16);
-    k_correction_literal<<<grid, block, 0, s>>>(h, dx, dz, n, out);
+    k_correction_literal<<<grid, block, 0, s>>>(h, dx, dz, n, out, out_pitch);
     return cudaGetLastError();
 }
 

@@ -13,8 +13,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (CorrectionLocals, OceanConfig, OceanError, PropagateLocals,  # noqa: F401
-                   PIPELINE_FUSED, PIPELINE_LITERAL)
+from ._lib import (CorrectionLocals, OceanConfig, OceanError, PropagateLocals, SpectrumParams,  # noqa: F401
+                   PIPELINE_FUSED, PIPELINE_LITERAL, FLAG_DOUBLE_BUFFER_OUTPUT)
 
 # src/render.rs:42-46
 WORKGROUP_SIZE = 16
@@ -69,6 +69,22 @@ class Ocean:
     def set_spectrum_device(self, tile: int, d_h0: int, d_omega: int) -> None:
         self._check(self._lib.ocean_set_spectrum_device(self._ctx, tile, d_h0, d_omega))
 
+    def generate_spectrum(self, tile: int, seed: int, stream_id: int | None = None, params: SpectrumParams | None = None,
+                          want_words: bool = False):
+        """Seeded Phillips / finite-depth inputs generated on the device (no upload). -> Philox words or None."""
+        n = self.resolution
+        words = np.empty((n, n, 4), np.uint32) if want_words else None
+        self._check(self._lib.ocean_generate_spectrum(self._ctx, tile, seed, tile if stream_id is None else stream_id,
+                                                      C.byref(params) if params is not None else None,
+                                                      words.ctypes.data if want_words else None))
+        return words
+
+    def get_spectrum(self, tile: int = 0):
+        n = self.resolution
+        h0, om = np.empty((n, n, 2), np.float32), np.empty((n, n), np.float32)
+        self._check(self._lib.ocean_get_spectrum(self._ctx, tile, h0.ctypes.data, om.ctypes.data))
+        return h0, om
+
     def load_bincode(self, tile: int, omega_path: str, spectrum_path: str) -> None:
         self._check(self._lib.ocean_load_bincode(self._ctx, tile, omega_path.encode(), spectrum_path.encode()))
 
@@ -79,6 +95,10 @@ class Ocean:
     def update_tiles(self, time: float, first_tile: int, count: int) -> None:
         self._check(self._lib.ocean_update_tiles(self._ctx, time, first_tile, count))
 
+    def update_graph(self, time: float, first_tile: int = 0, count: int | None = None) -> None:
+        """update_tiles through a recorded CUDA graph (replayed with `time` patched)."""
+        self._check(self._lib.ocean_update_graph(self._ctx, time, first_tile, self.n_tiles - first_tile if count is None else count))
+
     def update_sequence(self, t0: float, dt: float, n_frames: int) -> None:
         self._check(self._lib.ocean_update_sequence(self._ctx, t0, dt, n_frames))
 
@@ -88,6 +108,27 @@ class Ocean:
         cnt = C.c_uint32()
         self._check(self._lib.ocean_profile_update(self._ctx, time, buf, 8, C.byref(cnt)))
         return [float(buf[i]) for i in range(cnt.value)]
+
+    def update_sequence_checksums(self, t0: float, dt: float, n_frames: int) -> np.ndarray:
+        """Back-to-back frames; -> uint64[n_frames, n_tiles] checksums of every frame's maps."""
+        sums = np.zeros((n_frames, self.n_tiles), np.uint64)
+        self._check(self._lib.ocean_update_sequence_checksums(self._ctx, t0, dt, n_frames, sums.ctypes.data))
+        return sums
+
+    def output_checksums(self) -> np.ndarray:
+        sums = np.zeros(self.n_tiles, np.uint64)
+        self._check(self._lib.ocean_output_checksums(self._ctx, sums.ctypes.data))
+        return sums
+
+    def set_output_device(self, tile: int, d_rgba: int | None, row_pitch_bytes: int = 0) -> None:
+        """Renderer interop: write the tile's map into a caller-provided device allocation (None: own buffer)."""
+        self._check(self._lib.ocean_set_output_device(self._ctx, tile, d_rgba, row_pitch_bytes))
+
+    def read_back_all_async(self, host_ptr: int) -> None:
+        self._check(self._lib.ocean_download_all_async(self._ctx, host_ptr))
+
+    def download_fence(self, lag: int = 0) -> None:
+        self._check(self._lib.ocean_download_fence(self._ctx, lag))
 
     def sync(self) -> None:
         self._check(self._lib.ocean_sync(self._ctx))
@@ -124,6 +165,12 @@ class Ocean:
         n = self.resolution
         out = np.empty((n, n, 4), np.float32)
         self._check(self._lib.ocean_download_normals(self._ctx, tile, out.ctypes.data))
+        return out
+
+    def displace_grid(self, grid: int = 128, offset=(0.0, 0.0), tile: int = 0) -> np.ndarray:
+        """shader/ocean.vert:21-25 for the reference's vertex grid -> p_PosWorld[grid, grid, 3]."""
+        out = np.empty((grid, grid, 3), np.float32)
+        self._check(self._lib.ocean_displace_grid(self._ctx, tile, grid, offset[0], offset[1], out.ctypes.data))
         return out
 
     def debug_spectra(self, tile: int = 0):

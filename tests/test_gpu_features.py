@@ -1,0 +1,218 @@
+"""Round-2 GPU tests: the benchmarked configuration, PDL on/off bit-identity of EVERY frame, output routing
+(external / pitched buffers, double buffering), checksums / tile determinism, consumer kernels at all sizes."""
+import os
+
+import numpy as np
+import pytest
+
+from gfx_ocean_b200 import FLAG_DOUBLE_BUFFER_OUTPUT, Ocean, OceanError, PIPELINE_LITERAL, _lib
+from gfx_ocean_b200.spectrum import synthetic_tile
+from oracle.ocean_oracle import displace_grid_np, max_rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+class env:
+    """Set environment variables the library reads at context creation (OCEAN_B200_PDL / OCEAN_B200_ROWS)."""
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        for k, v in self.kv.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_benchmarked_configuration_every_tile_matches_oracle(oracle):
+    """bench.py's workload: 1024^2 x 8 tiles in ONE ocean_update; every tile against the f64 oracle."""
+    n, tiles, t = 1024, 8, 0.016 * 23
+    data = [synthetic_tile(n, g) for g in range(tiles)]
+    with Ocean(n, 1000.0, n_tiles=tiles) as o:
+        for i, (h0, w) in enumerate(data):
+            o.set_spectrum(i, h0, w)
+        o.update(t)
+        outs = [o.read_back(i) for i in range(tiles)]
+        sums = o.output_checksums()
+    for i, (h0, w) in enumerate(data):
+        errs = max_rel_err(outs[i], oracle.frame(h0, w, t, n, prec="f64"))
+        assert max(errs) <= TOL, (i, errs)
+        assert np.all(outs[i][..., 3] == 0.0)
+    assert len(set(int(s) for s in sums)) == tiles           # distinct tiles, distinct checksums
+
+
+@pytest.mark.parametrize("n,tiles,frames", [(512, 1, 600), (1024, 1, 500), (1024, 3, 120), (256, 2, 300)])
+def test_every_frame_is_bit_identical_with_and_without_pdl(n, tiles, frames):
+    """The hazard programmatic dependent launch could open: k_rows of frame n+1 overwriting the intermediate while
+    k_cols of frame n still reads it. The column kernel checksums what it stores, for EVERY frame of a back-to-back
+    sequence; PDL on, PDL off and the round-1 row kernel must agree bit for bit."""
+    data = [synthetic_tile(n, g) for g in range(tiles)]
+    sums = {}
+    for name, kv in (("pdl1", dict(OCEAN_B200_PDL="1")), ("pdl0", dict(OCEAN_B200_PDL="0")),
+                     ("legacy_pdl0", dict(OCEAN_B200_PDL="0", OCEAN_B200_ROWS="legacy"))):
+        with env(**kv):
+            with Ocean(n, 1000.0, n_tiles=tiles) as o:
+                for i, (h0, w) in enumerate(data):
+                    o.set_spectrum(i, h0, w)
+                sums[name] = o.update_sequence_checksums(0.0, 0.016, frames)
+                last = o.output_checksums()
+        np.testing.assert_array_equal(sums[name][-1], last)       # in-kernel checksum == reduction kernel's
+    np.testing.assert_array_equal(sums["pdl1"], sums["pdl0"])
+    assert len(np.unique(sums["pdl0"][:, 0])) == frames            # the frames do differ from each other
+
+
+def test_legacy_and_persistent_rows_agree_closely(oracle):
+    """Different summation order in the fold (fold-at-source vs per-line), same result to rounding."""
+    h0, w = synthetic_tile(1024, 5)
+    outs = []
+    for kv in (dict(OCEAN_B200_ROWS=None), dict(OCEAN_B200_ROWS="legacy")):
+        with env(**kv):
+            with Ocean.new(1024, 1000.0, w, h0) as o:
+                o.update(3.0)
+                outs.append(o.read_back())
+    assert max(max_rel_err(outs[0], outs[1])) <= 2e-6
+
+
+def test_tile_results_do_not_depend_on_batching_or_slot():
+    """tile i's result is bit-identical whatever the tile count / position in the context."""
+    n = 1024
+    data = [synthetic_tile(n, g) for g in range(4)]
+    with Ocean(n, 1000.0, n_tiles=4) as o:
+        for i, (h0, w) in enumerate(data):
+            o.set_spectrum(i, h0, w)
+        o.update(1.25)
+        batch = o.output_checksums()
+    single = []
+    for h0, w in data:
+        with Ocean.new(n, 1000.0, w, h0) as o:
+            o.update(1.25)
+            single.append(int(o.output_checksums()[0]))
+    assert [int(s) for s in batch] == single
+
+
+@pytest.mark.parametrize("pipeline", ["fused", "literal"])
+def test_external_pitched_output_buffer(pipeline):
+    """Renderer interop, CUDA half: the kernels write into a caller-provided (pitched) allocation."""
+    import torch
+    n = 512
+    h0, w = synthetic_tile(n, 1)
+    kw = dict(pipeline=PIPELINE_LITERAL) if pipeline == "literal" else {}
+    with Ocean.new(n, 1000.0, w, h0, **kw) as o:
+        o.update(2.0)
+        own = o.read_back()
+        pitch_texels = n + 48
+        ext = torch.full((n, pitch_texels, 4), -7.0, dtype=torch.float32, device="cuda")
+        o.set_output_device(0, ext.data_ptr(), pitch_texels * 16)
+        assert o.output() == ext.data_ptr()
+        o.update(2.0)
+        o.sync()
+        got = ext.cpu().numpy()
+        np.testing.assert_array_equal(got[:, :n], own)                # same bits, other destination
+        assert np.all(got[:, n:] == -7.0)                            # the padding is never written
+        np.testing.assert_array_equal(o.read_back(), own)            # download follows the routing (2-D copy)
+        o.compute_normals()
+        nrm_ext = o.read_back_normals()
+        dense = torch.zeros((n, n, 4), dtype=torch.float32, device="cuda")
+        o.set_output_device(0, dense.data_ptr(), 0)                   # dense external buffer: the product k_cols build
+        o.update(2.0)
+        o.sync()
+        np.testing.assert_array_equal(dense.cpu().numpy(), own)
+        o.set_output_device(0, None)                                  # back to the context's buffer
+        o.update(2.0)
+        np.testing.assert_array_equal(o.read_back(), own)
+        o.compute_normals()
+        np.testing.assert_array_equal(o.read_back_normals(), nrm_ext)
+        with pytest.raises(OceanError):
+            o.set_output_device(0, ext.data_ptr() + 4, 0)             # misaligned
+        with pytest.raises(OceanError):
+            o.set_output_device(0, ext.data_ptr(), n * 16 - 16)       # pitch too small
+
+
+def test_double_buffered_readback_pipeline():
+    import torch
+    n, tiles, frames = 512, 3, 12
+    data = [synthetic_tile(n, g) for g in range(tiles)]
+    ref = []
+    with Ocean(n, 1000.0, n_tiles=tiles) as o:
+        for i, (h0, w) in enumerate(data):
+            o.set_spectrum(i, h0, w)
+        for f in range(frames):
+            o.update(0.1 * f)
+            ref.append(np.stack([o.read_back(i) for i in range(tiles)]))
+    host = [torch.empty((tiles, n, n, 4), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    with Ocean(n, 1000.0, n_tiles=tiles, flags=FLAG_DOUBLE_BUFFER_OUTPUT) as o:
+        for i, (h0, w) in enumerate(data):
+            o.set_spectrum(i, h0, w)
+        for f in range(frames):
+            o.update(0.1 * f)
+            o.read_back_all_async(host[f % 2].data_ptr())
+            o.download_fence(1)                                       # frame f-1 is on the host now
+            if f >= 1:
+                np.testing.assert_array_equal(host[(f - 1) % 2].numpy(), ref[f - 1])
+        o.download_fence(0)
+        np.testing.assert_array_equal(host[(frames - 1) % 2].numpy(), ref[-1])
+        np.testing.assert_array_equal(o.read_back(1), ref[-1][1])     # per-tile download reads the current buffer
+        with pytest.raises(OceanError):
+            o.update_tiles(0.0, 0, 1)
+        with pytest.raises(OceanError):
+            o.set_output_device(0, 0)
+
+
+@pytest.mark.parametrize("n", [64, 256, 1024, 2048])
+def test_normal_map_all_sizes_and_tiles(n, oracle):
+    tiles = 2 if n <= 1024 else 1
+    data = [synthetic_tile(n, g + 20) for g in range(tiles)]
+    with Ocean(n, 1000.0, n_tiles=tiles) as o:
+        for i, (h0, w) in enumerate(data):
+            o.set_spectrum(i, h0, w)
+        o.update(0.75)
+        o.compute_normals()
+        for i in range(tiles):
+            disp, nrm = o.read_back(i), o.read_back_normals(i)
+            ref = oracle.normal_map(disp.astype(np.float64), prec="f64")
+            assert np.abs(nrm - ref).max() <= 1e-5
+            assert np.all(nrm[..., 3] == 0.0)
+
+
+@pytest.mark.parametrize("n,grid", [(512, 128), (1024, 128), (256, 257)])
+def test_displace_grid_matches_oracle(n, grid):
+    h0, w = synthetic_tile(n, 4)
+    with Ocean.new(n, 1000.0, w, h0) as o:
+        o.update(1.5)
+        disp = o.read_back()
+        pw = o.displace_grid(grid, (127.0, -3.0))
+    ref = displace_grid_np(disp, grid, (127.0, -3.0))
+    assert np.abs(pw - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_graph_replay_is_bit_identical_to_plain_launches():
+    n, tiles = 512, 3
+    data = [synthetic_tile(n, g + 40) for g in range(tiles)]
+    with Ocean(n, 1000.0, n_tiles=tiles) as o:
+        for i, (h0, w) in enumerate(data):
+            o.set_spectrum(i, h0, w)
+        plain, graph = [], []
+        for f in range(6):
+            o.update(0.3 * f)
+            plain.append(o.output_checksums())
+        l0 = o.launch_count
+        for f in range(6):
+            o.update_graph(0.3 * f)
+            graph.append(o.output_checksums())
+        assert o.launch_count - l0 == 6 * (2 + tiles)          # 2 kernels per replayed frame (+ the checksum kernels)
+        np.testing.assert_array_equal(np.array(plain), np.array(graph))
+        o.update_tiles(0.9, 1, 2)
+        a = o.output_checksums()
+        o.update(0.0)
+        o.update_graph(0.9, 1, 2)                               # another tile range: another recorded graph
+        np.testing.assert_array_equal(o.output_checksums()[1:], a[1:])
