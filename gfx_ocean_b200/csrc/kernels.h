@@ -34,6 +34,7 @@ struct FusedPlan;
 bool fused_supports(uint32_t n);
 cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, float domain_size, int device);
 void fused_plan_destroy(FusedPlan* p);
+void fused_plan_intermediate(const FusedPlan* p, uint32_t tile, const float2** gp, size_t* gp_count, const float2** gh, size_t* gh_count);
 // Where tile t's displacement map goes: the context's own buffer or a caller-provided (e.g. imported Vulkan)
 // allocation. One record per tile, in device memory.
 struct OutDesc {

@@ -587,6 +587,7 @@ k_rows_p(const float2* __restrict__ h0_all, const float* __restrict__ omega_all,
                 fold_pair<Cfg, false>(bx * PAIRS + p, R, R + N, R + 2 * N, R + 3 * N, W, W + N, kx_g, time, L0, L0 + Cfg::LINE,
                                       L0 + 2 * Cfg::LINE, gt, GT, [](const float2* q) { return *q; }, [](const float* q) { return *q; });
             }
+            ptx::fence_proxy_async();             // generic reads of the slot precede the bulk copy that refills it
             ptx::mbar_arrive(empty + slot);       // this thread's reads of the slot are done
         } else {
             const float2* __restrict__ h0 = h0_all + size_t(first_tile + tl) * N * N;
@@ -757,7 +758,14 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                 const uint32_t tl = item / STRIPS, strip = item % STRIPS;
                 const float2* srcH = gh_all + size_t(tl) * IL::H_TILE + size_t(strip) * IL::H_STRIP;
                 const float2* srcP = gp_all + size_t(tl) * IL::P_TILE + size_t(strip) * IL::P_STRIP;
-                if (it >= 1) ptx::mbar_wait_backoff(emptyG, (it - 1) & 1);
+                if (it >= 1) {
+                    ptx::mbar_wait_backoff(emptyG, (it - 1) & 1);
+                    // The height warps read GB through the generic proxy; the copy below writes it through the async
+                    // proxy. The mbarrier orders generic accesses only: without this fence the copy can overtake
+                    // reads that are still in flight (seen in round 2 as sporadically wrong height strips once a block
+                    // processes four or more strips -- 1024^2 x 4+ tiles per launch; the intermediate was identical).
+                    ptx::fence_proxy_async();
+                }
                 ptx::mbar_arrive_expect_tx(fullG, CC::H_BYTES);
                 ptx::bulk_g2s(GB, srcH, CC::H_BYTES, fullG);
                 const uint32_t b = it & 1;
@@ -813,6 +821,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                     else v[k1] = make_float2(g.x + g.w, g.z - g.y);
                 }
             }
+            ptx::fence_proxy_async();          // this thread's generic reads of GB precede the next bulk copy into it
             ptx::mbar_arrive(emptyG);
             RegFft<R1>::run(v);
 #pragma unroll
@@ -854,6 +863,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                 (void)waited;
                 ptx::named_bar_sync<2, NTH>();                          // XH drained: the next item may overwrite it
             }
+            ptx::fence_proxy_async();          // HR lives in PB[b], which the async proxy refills two items later
             ptx::mbar_arrive(hrReady);
         }
     } else {
@@ -974,6 +984,7 @@ struct FusedPlan {
     float* d_kx = nullptr;       // [N] wave numbers, propagate.comp:45-46,50-53
     float2* d_gp = nullptr;      // [tiles] strip-major packed (dx, dz) row-pass output
     float2* d_gh = nullptr;      // [tiles] strip-major height row-pass output (N/2 rows)
+    size_t gp_per_tile = 0, gh_per_tile = 0;   // float2 per tile
 };
 
 template <int N, int P, int PAIRS, int C, int MINB, int PPAIRS, int GROUPS, int SLOTS>
@@ -1020,7 +1031,11 @@ struct Launch {
         const float* kx = p->d_kx;
         float2 *gp = p->d_gp, *gh = p->d_gh;
         cudaError_t e;
-        if (p->rows_legacy) {
+        static const bool debug_env = std::getenv("OCEAN_B200_DEBUG") != nullptr;
+        const bool skip_rows = debug_env && std::getenv("OCEAN_B200_DEBUG_SKIP_ROWS") != nullptr;   // re-run k_cols on the same intermediate
+        if (skip_rows) {
+            e = cudaSuccess;
+        } else if (p->rows_legacy) {
             // measured on B200 (N=1024): PDL gains 21% / 7% at 1 / 4 tiles per launch (it hides ramp and tail) and
             // loses 1.5-3.5% at 8-16 tiles, so it is used while the row grid is below four waves
             const bool pdl = p->pdl_mode == 1 || (p->pdl_mode < 0 && (N / 2 / PAIRS) * count < 4u * uint32_t(p->num_sms) * MINB);
@@ -1164,6 +1179,8 @@ cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, flo
         default: gp_t = L2048::gp_floats2_per_tile(); gh_t = L2048::gh_floats2_per_tile(); e = L2048::prepare(p); break;
     }
     if (e != cudaSuccess) return bail(e);
+    p->gp_per_tile = gp_t;
+    p->gh_per_tile = gh_t;
     // pad rows of the intermediate are never written by k_rows but are copied (and ignored) by k_cols: zero them once
     if ((e = cudaMalloc(&p->d_gp, size_t(n_tiles) * gp_t * sizeof(float2))) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc(&p->d_gh, size_t(n_tiles) * gh_t * sizeof(float2))) != cudaSuccess) return bail(e);
@@ -1171,6 +1188,15 @@ cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, flo
     if ((e = cudaMemset(p->d_gh, 0, size_t(n_tiles) * gh_t * sizeof(float2))) != cudaSuccess) return bail(e);
     *out = p;
     return cudaSuccess;
+}
+
+// debug: the row-pass output of tile `tile` as raw float2 ranges (tests / hazard hunting only)
+void fused_plan_intermediate(const FusedPlan* p, uint32_t tile, const float2** gp, size_t* gp_count, const float2** gh, size_t* gh_count)
+{
+    *gp = p->d_gp + size_t(tile) * p->gp_per_tile;
+    *gh = p->d_gh + size_t(tile) * p->gh_per_tile;
+    *gp_count = p->gp_per_tile;
+    *gh_count = p->gh_per_tile;
 }
 
 void fused_plan_destroy(FusedPlan* p)

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -535,8 +536,22 @@ int ocean_output_checksums(ocean_ctx* c, uint64_t* h_sums)
     OCEAN_ON_DEVICE(c);
     if (int rc = ensure_sums(c, c->n_tiles)) return rc;
     OCEAN_CUDA(c, cudaMemsetAsync(c->d_sums, 0, c->n_tiles * sizeof(unsigned long long), c->stream));
-    for (uint32_t t = 0; t < c->n_tiles; ++t)
-        OCEAN_CUDA(c, ocean::launch_checksum(tile_out(c, t), tile_pitch(c, t), c->n, c->d_sums + t, c->stream));
+    const char* dbg = std::getenv("OCEAN_B200_DEBUG") ? std::getenv("OCEAN_B200_DEBUG_INTER") : nullptr;
+    for (uint32_t t = 0; t < c->n_tiles; ++t) {
+        if (dbg && c->plan) {
+            // hazard hunting: checksum the row-pass output (gp or gh) instead of the displacement map
+            const float2 *gp, *gh;
+            size_t ngp, ngh;
+            ocean::fused_plan_intermediate(c->plan, t, &gp, &ngp, &gh, &ngh);
+            const float2* src = dbg[0] == 'h' ? gh : gp;
+            const size_t n4 = (dbg[0] == 'h' ? ngh : ngp) / 2;         // float4 count
+            const uint32_t side = 512;
+            OCEAN_CUDA(c, ocean::launch_checksum(reinterpret_cast<const float4*>(src), side, side, c->d_sums + t, c->stream));
+            (void)n4;
+        } else {
+            OCEAN_CUDA(c, ocean::launch_checksum(tile_out(c, t), tile_pitch(c, t), c->n, c->d_sums + t, c->stream));
+        }
+    }
     c->launches += c->n_tiles;
     OCEAN_CUDA(c, cudaMemcpyAsync(h_sums, c->d_sums, c->n_tiles * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     OCEAN_CUDA(c, cudaStreamSynchronize(c->stream));

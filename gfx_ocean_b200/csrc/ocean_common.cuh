@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace ocean {
 
@@ -52,7 +53,8 @@ __device__ __forceinline__ float2 unit_wave_vector_fast(float kx, float ky)
 // Full-range sincos for the propagation phase omega*t (which reaches 1e3..1e4 rad).
 // |x| <= 1e5: Cody-Waite reduction by pi/2 in three FMA steps (constants sum to pi/2 within
 // 3.3e-22) + degree-7/8 minimax polynomials on [-pi/4, pi/4]; max abs error 7e-8 (measured
-// against f64 over 1.6M samples, tests/test_host_fft.py). Larger arguments take libdevice's
+// against f64 over 2M samples by tests/test_host_fft.py::test_sincos_reduced_accuracy, which compiles this
+// header for the host). Larger arguments take libdevice's
 // Payne-Hanek path, kept out of line so the unrolled callers stay small.
 static __device__ __noinline__ float2 sincos_huge(float x)
 {
@@ -61,10 +63,15 @@ static __device__ __noinline__ float2 sincos_huge(float x)
     return make_float2(s, c);
 }
 
-__device__ __forceinline__ void sincos_reduced(float x, float& sn, float& cs)
+__host__ __device__ __forceinline__ void sincos_reduced(float x, float& sn, float& cs)
 {
     float j = fmaf(x, 0.636619747f, 12582912.f);     // 1.5 * 2^23: rint(x * 2/pi) in the low mantissa bits
+#ifdef __CUDA_ARCH__
     const int q = __float_as_int(j);
+#else
+    int q;
+    memcpy(&q, &j, sizeof q);
+#endif
     j -= 12582912.f;
     float r = fmaf(j, -1.57079601e+00f, x);
     r = fmaf(j, -3.13916473e-07f, r);
@@ -83,9 +90,25 @@ __device__ __forceinline__ void sincos_reduced(float x, float& sn, float& cs)
     cs = ((q + 1) & 2) ? -co : co;
 }
 
+// A/B variant (-DOCEAN_SINCOS_MUFU): Cody-Waite reduction by 2 pi (the same three constants, times four) to
+// [-pi, pi], then the special-function unit: 9 instructions instead of ~30, absolute error ~4e-7 instead of 7e-8.
+__device__ __forceinline__ void sincos_mufu(float x, float& sn, float& cs)
+{
+    const float n = fmaf(x, 0.159154943f, 12582912.f) - 12582912.f;       // rint(x / 2 pi)
+    float r = fmaf(n, -6.28318405e+00f, x);
+    r = fmaf(n, -1.25566589e-06f, r);
+    r = fmaf(n, -2.15612101e-14f, r);
+    sn = __sinf(r);
+    cs = __cosf(r);
+}
+
 __device__ __forceinline__ void sincos_full(float x, float& sn, float& cs)
 {
+#ifdef OCEAN_SINCOS_MUFU
+    if (fabsf(x) <= 1.0e5f) sincos_mufu(x, sn, cs);
+#else
     if (fabsf(x) <= 1.0e5f) sincos_reduced(x, sn, cs);
+#endif
     else {
         const float2 sc = sincos_huge(x);
         sn = sc.x;
