@@ -48,9 +48,21 @@ pub struct ocean_config {
     pub flags: u32,
 }
 
-pub const OCEAN_B200_ABI_VERSION: u32 = 1;
+pub const OCEAN_B200_ABI_VERSION: u32 = 2;
 pub const OCEAN_PIPELINE_FUSED: u32 = 0;
 pub const OCEAN_PIPELINE_LITERAL: u32 = 1;
+pub const OCEAN_FLAG_KEEP_SPECTRA: u32 = 1;
+pub const OCEAN_FLAG_DOUBLE_BUFFER_OUTPUT: u32 = 2;
+
+/// Parameters of `ocean_generate_spectrum` (NULL: amplitude 3e-8, wind 30 m/s, g 9.81, depth 100 m).
+#[repr(C)]
+#[derive(Debug, Clone, Copy)]
+pub struct ocean_spectrum_params {
+    pub amplitude: f32,
+    pub wind_speed: f32,
+    pub gravity: f32,
+    pub depth: f32,
+}
 
 extern "C" {
     pub fn ocean_create(out: *mut *mut ocean_ctx, cuda_device: c_int, resolution: u32, domain_size: f32, n_tiles: u32) -> c_int;
@@ -59,9 +71,19 @@ extern "C" {
     pub fn ocean_set_spectrum(ctx: *mut ocean_ctx, tile: u32, h0_xy: *const f32, omega: *const f32) -> c_int;
     pub fn ocean_set_spectrum_device(ctx: *mut ocean_ctx, tile: u32, d_h0_xy: *const f32, d_omega: *const f32) -> c_int;
     pub fn ocean_load_bincode(ctx: *mut ocean_ctx, tile: u32, omega_path: *const c_char, spectrum_path: *const c_char) -> c_int;
+    pub fn ocean_generate_spectrum(ctx: *mut ocean_ctx, tile: u32, seed: u64, stream_id: u32, params: *const ocean_spectrum_params, h_words: *mut u32) -> c_int;
+    pub fn ocean_get_spectrum(ctx: *mut ocean_ctx, tile: u32, h0_xy: *mut f32, omega: *mut f32) -> c_int;
     pub fn ocean_update(ctx: *mut ocean_ctx, time: f32) -> c_int;
     pub fn ocean_update_tiles(ctx: *mut ocean_ctx, time: f32, first_tile: u32, count: u32) -> c_int;
+    pub fn ocean_update_graph(ctx: *mut ocean_ctx, time: f32, first_tile: u32, count: u32) -> c_int;
     pub fn ocean_update_sequence(ctx: *mut ocean_ctx, t0: f32, dt: f32, n_frames: u32) -> c_int;
+    pub fn ocean_update_sequence_checksums(ctx: *mut ocean_ctx, t0: f32, dt: f32, n_frames: u32, h_sums: *mut u64) -> c_int;
+    pub fn ocean_output_checksums(ctx: *mut ocean_ctx, h_sums: *mut u64) -> c_int;
+    pub fn ocean_set_output_device(ctx: *mut ocean_ctx, tile: u32, d_rgba: *mut f32, row_pitch_bytes: usize) -> c_int;
+    pub fn ocean_displace_grid(ctx: *mut ocean_ctx, tile: u32, grid: u32, offset_x: f32, offset_z: f32, h_pos_world: *mut f32) -> c_int;
+    pub fn ocean_displace_grid_device(ctx: *mut ocean_ctx, tile: u32, grid: u32, offset_x: f32, offset_z: f32, d_pos_world: *mut f32) -> c_int;
+    pub fn ocean_download_all_async(ctx: *mut ocean_ctx, h_rgba_all: *mut f32) -> c_int;
+    pub fn ocean_download_fence(ctx: *mut ocean_ctx, lag: u32) -> c_int;
     pub fn ocean_compute_normals(ctx: *mut ocean_ctx, first_tile: u32, count: u32) -> c_int;
     pub fn ocean_normals_device(ctx: *mut ocean_ctx, tile: u32, d_nrm: *mut *const f32) -> c_int;
     pub fn ocean_download_normals(ctx: *mut ocean_ctx, tile: u32, h_nrm: *mut f32) -> c_int;
@@ -147,6 +169,22 @@ impl Ocean {
     pub fn read_back(&self, dst: &mut [[f32; 4]]) -> Result<(), OceanError> {
         assert_eq!(dst.len(), (self.resolution as usize).pow(2));
         let rc = unsafe { ocean_download(self.ctx, 0, dst.as_mut_ptr() as *mut f32) };
+        if rc != 0 { Err(Self::err(self.ctx, rc)) } else { Ok(()) }
+    }
+
+    /// Renderer interop (src/render.rs:820-869, :939): have the kernels write the displacement map straight into
+    /// device memory the renderer owns -- the linear image / buffer it exported with VK_KHR_external_memory_fd and
+    /// imported with cudaImportExternalMemory. `row_pitch_bytes` = the image's row pitch (0 = dense N*16).
+    pub unsafe fn set_output(&mut self, d_rgba: *mut [f32; 4], row_pitch_bytes: usize) -> Result<(), OceanError> {
+        let rc = ocean_set_output_device(self.ctx, 0, d_rgba as *mut f32, row_pitch_bytes);
+        if rc != 0 { Err(Self::err(self.ctx, rc)) } else { Ok(()) }
+    }
+
+    /// p_PosWorld of shader/ocean.vert:21-25 for the `grid` x `grid` vertex patch of src/render.rs:498-506 with the
+    /// patch offset of :540-551 (HALF_RESOLUTION = 128).
+    pub fn displace_grid(&self, grid: u32, offset: [f32; 2], dst: &mut [[f32; 3]]) -> Result<(), OceanError> {
+        assert_eq!(dst.len(), (grid as usize).pow(2));
+        let rc = unsafe { ocean_displace_grid(self.ctx, 0, grid, offset[0], offset[1], dst.as_mut_ptr() as *mut f32) };
         if rc != 0 { Err(Self::err(self.ctx, rc)) } else { Ok(()) }
     }
 

@@ -7,6 +7,7 @@
 // constants of src/render.rs:42-46, and an `Ocean` with new/update/output/read_back in place of
 // the Propagation<B>/Fft<B>/Correction<B> holders + the dispatch code of Renderer::render().
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -64,6 +65,21 @@ public:
         const float* p = nullptr;
         const_cast<Ocean*>(this)->check(ocean_output_device(ctx_, 0, &p));
         return p;
+    }
+    // renderer interop: write the map into a caller-provided (e.g. imported Vulkan) allocation, pitch in bytes (0: dense)
+    void set_output(float* d_rgba, size_t row_pitch_bytes = 0) { check(ocean_set_output_device(ctx_, 0, d_rgba, row_pitch_bytes)); }
+    // shader/ocean.vert:21-25 for the grid x grid vertex patch (src/render.rs:498-506) -> p_PosWorld[grid*grid*3]
+    std::vector<float> displace_grid(uint32_t grid, float offset_x, float offset_z)
+    {
+        std::vector<float> v(size_t(3) * grid * grid);
+        check(ocean_displace_grid(ctx_, 0, grid, offset_x, offset_z, v.data()));
+        return v;
+    }
+    uint64_t checksum()
+    {
+        uint64_t s = 0;
+        check(ocean_output_checksums(ctx_, &s));
+        return s;
     }
     void read_back(float* rgba) { check(ocean_download(ctx_, 0, rgba)); }
     std::vector<float> read_back()

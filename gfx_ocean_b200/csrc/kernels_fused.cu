@@ -1,7 +1,15 @@
 // The product path: two fused sm_100a kernels per frame.
 //
 //   k_rows  = propagate (shader/propagate.comp:42-72) + Hermitian fold + row transforms
-//             (shader/fft_row.comp:44-63 for the three fields)
+//             (shader/fft_row.comp:44-63 for the three fields). Three implementations of the same arithmetic:
+//             k_rows_t "tma" (default): one block per row pair; one thread bulk-copies (cp.async.bulk / TMA) the pair's
+//                      raw rows into shared memory, the propagated (h, khat) records overwrite them in place, each line
+//                      warp folds its own inputs. Always launched with programmatic dependent launch.
+//             k_rows   "staged": round 1's kernel, the same with register-staged 128-bit global loads.
+//             k_rows_p "persistent" / "fold": fold at the source -- the thread that owns x evaluates both points of a
+//                      fold and writes the three folded sequences directly -- as a persistent kernel with a bulk-copy fed
+//                      raw-row ring (or an L2-prefetch warp), or with one unit per block. A third of the shared-memory
+//                      traffic, but slower on B200: kept as measured alternatives.
 //   k_cols  = column transforms (shader/fft_col.comp:44-63) + sign correction + RGBA pack
 //             (shader/correction.comp:24-35)
 //
@@ -128,14 +136,74 @@ __device__ __forceinline__ float2 rot_mul_conj(float4 s)
     return make_float2(fmaf(s.w, s.x, -s.z * s.y), -fmaf(s.w, s.y, s.z * s.x));
 }
 
+// Second half of a row line, shared by the row kernels that stage propagated rows (k_rows, k_rows_t): pass 1 in
+// registers on the folded inputs v, twiddle, exchange through the line, pass 2 (and 3), strip-major stores.
+template <int N, int P, int C>
+__device__ __forceinline__ void rows_line_finish(float2 (&v)[LineCfg<N, P>::R1], float2* line, int k2, int seq, uint32_t j,
+                                                 const float2* __restrict__ tw_g, float2* __restrict__ gp, float2* __restrict__ gh)
+{
+    using Cfg = LineCfg<N, P>;
+    using IL = Inter<N, C, Cfg::GS>;
+    constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2;
+    const bool self_paired = (j == 0);
+    RegFft<R1>::run(v);
+#pragma unroll
+    for (int n1 = 0; n1 < R1; ++n1) {
+        const float2 y = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * T + k2));
+        line[Cfg::pad(n1 * T + k2)] = y;
+    }
+    if constexpr (T <= 32) __syncwarp(); else __syncthreads();
+    // The intermediate is still being read by the previous frame's k_cols until that grid has completed: every
+    // storing block waits itself (no assumption on block dispatch order; ~0.3 us per block, +2 % on the kernel).
+    pdl_wait_prior_grid();
+
+    // Destination row in the strip-major intermediate. Thread n1 owns columns n = n1 + R1 n2: strip n / C and
+    // in-strip column n % C advance by a constant per n2 (R1 is a multiple of C), also for the mirrored
+    // sequence, whose column (N - n) mod N runs backwards; only n = 0 maps to itself there.
+    static_assert(R1 % C == 0, "pass-1 radix must cover whole strips");
+    float2* dst;
+    bool mirrored = false;
+    if (seq == 0) dst = gp + IL::row_off(j);
+    else if (seq == 1) { dst = gp + IL::row_off(self_paired ? N / 2 : N - j); mirrored = !self_paired; }
+    else dst = gh + IL::row_off(j);
+    const long strip_stride = seq == 2 ? IL::H_STRIP : IL::P_STRIP;
+    if constexpr (Cfg::R3 > 1) {
+        line_passes_23<Cfg>(line, k2, tw_g + N, [] { __syncthreads(); }, [&](int n, float2 val) {
+            const uint32_t col = mirrored ? ((N - n) & (N - 1)) : n;
+            dst[long(col / C) * strip_stride + col % C] = val;
+        });
+        return;
+    }
+    const long step = (mirrored ? -long(R1 / C) : long(R1 / C)) * strip_stride;
+#pragma unroll
+    for (int i = 0; i < Cfg::SUB2; ++i) {
+        const int n1 = k2 + R2 * i;
+        float2 u[R2];
+#pragma unroll
+        for (int k = 0; k < R2; ++k) u[k] = line[Cfg::pad(n1 * R2 + k)];
+        RegFft<R2>::run(u);
+        const uint32_t col0 = mirrored ? ((N - n1) & (N - 1)) : n1;          // column of n2 = 0
+        float2* q = dst + long(col0 / C) * strip_stride + col0 % C;
+        if (mirrored && n1 == 0) {
+            q[0] = u[0];                                                       // n = 0 -> column 0
+            q += long(N / C) * strip_stride;                                   // n = R1 n2 -> column N - R1 n2
+#pragma unroll
+            for (int n2 = 1; n2 < R2; ++n2) q[n2 * step] = u[n2];
+        } else {
+#pragma unroll
+            for (int n2 = 0; n2 < R2; ++n2) q[n2 * step] = u[n2];
+        }
+    }
+}
+
 template <int N, int P, int PAIRS, int C, int MINB>
 __global__ void __launch_bounds__(3 * PAIRS * (N / P), MINB)
 k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, const float2* __restrict__ tw_g,
        const float* __restrict__ kx_g, float2* __restrict__ gp_all, float2* __restrict__ gh_all, float time,
-       uint32_t first_tile, uint32_t resident_blocks)
+       uint32_t first_tile, uint32_t /*unused*/)
 {
     using Cfg = LineCfg<N, P>;
-    constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2;
+    constexpr int T = Cfg::T, R1 = Cfg::R1;
     constexpr int NT = 3 * PAIRS * T;
     constexpr int NROWS = 2 * PAIRS;
     constexpr int SP = N + 1;             // row pitch of S: element N duplicates element 0, so S[N - x] is -x mod N
@@ -244,55 +312,7 @@ k_rows(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, c
         }
     }
     __syncthreads();                      // every warp has its inputs: S may be overwritten by the lines
-    RegFft<R1>::run(v);
-#pragma unroll
-    for (int n1 = 0; n1 < R1; ++n1) {
-        const float2 y = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * T + k2));
-        line[Cfg::pad(n1 * T + k2)] = y;
-    }
-    if constexpr (T <= 32) __syncwarp(); else __syncthreads();
-    // The intermediate is still being read by the previous frame's k_cols until that grid has completed. Only
-    // blocks that can be resident before any block of this grid has exited need to wait: every later block
-    // starts after an earlier one has passed this point (griddepcontrol.wait costs ~0.3 us even when satisfied).
-    if (blockIdx.x + gridDim.x * blockIdx.y < resident_blocks) pdl_wait_prior_grid();
-
-    // Destination row in the strip-major intermediate. Thread n1 owns columns n = n1 + R1 n2: strip n / C and
-    // in-strip column n % C advance by a constant per n2 (R1 is a multiple of C), also for the mirrored
-    // sequence, whose column (N - n) mod N runs backwards; only n = 0 maps to itself there.
-    static_assert(R1 % C == 0, "pass-1 radix must cover whole strips");
-    float2* dst;
-    bool mirrored = false;
-    if (seq == 0) dst = gp + IL::row_off(j);
-    else if (seq == 1) { dst = gp + IL::row_off(self_paired ? N / 2 : N - j); mirrored = !self_paired; }
-    else dst = gh + IL::row_off(j);
-    const long strip_stride = seq == 2 ? IL::H_STRIP : IL::P_STRIP;
-    if constexpr (Cfg::R3 > 1) {
-        line_passes_23<Cfg>(line, k2, tw_g + N, [] { __syncthreads(); }, [&](int n, float2 val) {
-            const uint32_t col = mirrored ? ((N - n) & (N - 1)) : n;
-            dst[long(col / C) * strip_stride + col % C] = val;
-        });
-        return;
-    }
-    const long step = (mirrored ? -long(R1 / C) : long(R1 / C)) * strip_stride;
-#pragma unroll
-    for (int i = 0; i < Cfg::SUB2; ++i) {
-        const int n1 = k2 + R2 * i;
-        float2 u[R2];
-#pragma unroll
-        for (int k = 0; k < R2; ++k) u[k] = line[Cfg::pad(n1 * R2 + k)];
-        RegFft<R2>::run(u);
-        const uint32_t col0 = mirrored ? ((N - n1) & (N - 1)) : n1;          // column of n2 = 0
-        float2* q = dst + long(col0 / C) * strip_stride + col0 % C;
-        if (mirrored && n1 == 0) {
-            q[0] = u[0];                                                       // n = 0 -> column 0
-            q += long(N / C) * strip_stride;                                   // n = R1 n2 -> column N - R1 n2
-#pragma unroll
-            for (int n2 = 1; n2 < R2; ++n2) q[n2 * step] = u[n2];
-        } else {
-#pragma unroll
-            for (int n2 = 0; n2 < R2; ++n2) q[n2 * step] = u[n2];
-        }
-    }
+    rows_line_finish<N, P, C>(v, line, k2, seq, j, tw_g, gp, gh);
 }
 
 
@@ -354,6 +374,169 @@ __device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1
 }  // namespace ptx
 
 // ------------------------------------------------------------------------------------------
+// k_rows_t: the staged row kernel fed by bulk copies (TMA), records written in place
+// ------------------------------------------------------------------------------------------
+// Same block shape and phase B as k_rows. Phase A's global loads are replaced by cp.async.bulk: at block start one
+// thread copies, per row, the forward row of h0, its reversed partner row and the row of omega into shared memory
+// (one mbarrier, one memory round trip for everything, no register staging). The propagated records then overwrite
+// the raw rows they were computed from: H[x] = h(x) goes where h0(x) was, K[x] = khat(x) where the thread's partner
+// h0(N-1-x) was (so K is stored reversed). Per row: [FWD: N+2 float2][REV: N+2 float2][OM: N float]; FWD[N] duplicates
+// H[0] and the slot before REV duplicates K[0], so that index N means 0 for both (the -x mod N of the folds).
+#ifndef OCEAN_ROWS_T_PREFETCH
+#define OCEAN_ROWS_T_PREFETCH 0
+#endif
+template <int N>
+struct RowSlot {
+    static constexpr uint32_t REV_OFF = 8u * (N + 2), OM_OFF = 16u * (N + 2), BYTES = OM_OFF + 4u * N;
+    static_assert(REV_OFF % 16 == 0 && BYTES % 16 == 0, "bulk copies need 16-byte granules");
+    unsigned char* base;
+    __device__ __forceinline__ float2* fwd() const { return reinterpret_cast<float2*>(base); }
+    __device__ __forceinline__ float2* rev() const { return reinterpret_cast<float2*>(base + REV_OFF); }
+    __device__ __forceinline__ float* om() const { return reinterpret_cast<float*>(base + OM_OFF); }
+    // after phase A: record i in [0, N]
+    __device__ __forceinline__ float2 h(int i) const { return fwd()[i]; }
+    __device__ __forceinline__ float4 rec(int i) const
+    {
+        const float2 a = fwd()[i], k = rev()[N - 1 - i];
+        return make_float4(a.x, a.y, k.x, k.y);
+    }
+};
+
+template <int N, int P, int PAIRS, int C, int MINB>
+__global__ void __launch_bounds__(3 * PAIRS * (N / P), MINB)
+k_rows_t(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, const float2* __restrict__ tw_g,
+         const float* __restrict__ kx_g, float2* __restrict__ gp_all, float2* __restrict__ gh_all, float time, uint32_t first_tile)
+{
+    using Cfg = LineCfg<N, P>;
+    using Slot = RowSlot<N>;
+    constexpr int T = Cfg::T, R1 = Cfg::R1;
+    constexpr int NT = 3 * PAIRS * T;
+    constexpr int NROWS = 2 * PAIRS;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* X = reinterpret_cast<float2*>(smem_raw);                     // [3 PAIRS][LINE], reuses the slots after phase B's loads
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + NROWS * Slot::BYTES);
+    static_assert(sizeof(float2) * 3 * PAIRS * Cfg::LINE <= NROWS * Slot::BYTES, "exchange lines must fit in the slots");
+
+    const uint32_t tile = first_tile + blockIdx.y;
+    const float2* __restrict__ h0 = h0_all + size_t(tile) * N * N;
+    const float* __restrict__ omega = omega_all + size_t(tile) * N * N;
+    using IL = Inter<N, C, Cfg::GS>;
+    float2* __restrict__ gp = gp_all + size_t(blockIdx.y) * IL::P_TILE;
+    float2* __restrict__ gh = gh_all + size_t(blockIdx.y) * IL::H_TILE;
+
+    const int tid = threadIdx.x;
+    pdl_launch_dependents();
+    auto row_of = [&](int slot) -> uint32_t {
+        const uint32_t jp = blockIdx.x * PAIRS + (slot >> 1);            // pair index, 0 = the self-paired rows 0, N/2
+        return jp == 0 ? ((slot & 1) ? N / 2 : 0) : ((slot & 1) ? N - jp : jp);
+    };
+    if (tid == 0) {
+        ptx::mbar_init(bar, 1);
+        ptx::fence_mbar_init();
+        // h0 / omega are never written by a frame kernel: no griddepcontrol.wait before reading them
+        ptx::mbar_arrive_expect_tx(bar, NROWS * (2 * N * sizeof(float2) + N * sizeof(float)));
+        for (int slot = 0; slot < NROWS; ++slot) {
+            const uint32_t r = row_of(slot);
+            const Slot sl{smem_raw + slot * Slot::BYTES};
+            ptx::bulk_g2s(sl.fwd(), h0 + size_t(r) * N, N * sizeof(float2), bar);                 // propagate.comp:43
+            ptx::bulk_g2s(sl.rev(), h0 + size_t(N - 1 - r) * N, N * sizeof(float2), bar);         // :48, read reversed below
+            ptx::bulk_g2s(sl.om(), omega + size_t(r) * N, N * sizeof(float), bar);
+        }
+    }
+#if OCEAN_ROWS_T_PREFETCH > 0
+    {
+        // While this block waits for its own rows, pull the rows of the block that will run about one wave later from
+        // DRAM into L2, so that its bulk copies are L2 hits (blocks are dispatched roughly in linear order).
+        const uint32_t lin = blockIdx.x + gridDim.x * blockIdx.y + OCEAN_ROWS_T_PREFETCH;
+        if (lin < gridDim.x * gridDim.y) {
+            const uint32_t pbx = lin % gridDim.x, pby = lin / gridDim.x;
+            const char* ph0 = reinterpret_cast<const char*>(h0_all + size_t(first_tile + pby) * N * N);
+            const char* pom = reinterpret_cast<const char*>(omega_all + size_t(first_tile + pby) * N * N);
+            for (int slot = 0; slot < NROWS; ++slot) {
+                const uint32_t jp = pbx * PAIRS + (slot >> 1);
+                const uint32_t r = jp == 0 ? ((slot & 1) ? N / 2 : 0) : ((slot & 1) ? N - jp : jp);
+                for (uint32_t o = tid * 128; o < N * sizeof(float2); o += NT * 128) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ph0 + size_t(r) * N * sizeof(float2) + o));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ph0 + size_t(N - 1 - r) * N * sizeof(float2) + o));
+                }
+                for (uint32_t o = tid * 128; o < N * sizeof(float); o += NT * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pom + size_t(r) * N * sizeof(float) + o));
+            }
+        }
+    }
+#endif
+    __syncthreads();                      // the barrier is initialised before anyone polls it
+    ptx::mbar_wait(bar, 0);
+
+    // ---- phase A: propagate.comp, in place. A thread takes point pairs x = 2 (tid + k NT).
+#pragma unroll 1
+    for (int slot = 0; slot < NROWS; ++slot) {
+        const Slot sl{smem_raw + slot * Slot::BYTES};
+        const float ky = __ldg(kx_g + row_of(slot));
+        float4* F4 = reinterpret_cast<float4*>(sl.fwd());
+        float4* R4 = reinterpret_cast<float4*>(sl.rev());
+        const float2* W2 = reinterpret_cast<const float2*>(sl.om());
+        const float2* __restrict__ pk = reinterpret_cast<const float2*>(kx_g);
+#pragma unroll 2
+        for (int i = tid; i < N / 2; i += NT) {
+            const float4 a = F4[i], b = R4[N / 2 - 1 - i];     // b.zw is the partner of x = 2 i, b.xy the partner of x + 1
+            const float2 w = W2[i], kx = __ldg(pk + i);
+            const float2 h_0 = propagate_point_fast(make_float2(a.x, a.y), make_float2(b.z, b.w), w.x, time);
+            const float2 h_1 = propagate_point_fast(make_float2(a.z, a.w), make_float2(b.x, b.y), w.y, time);
+            const float2 k_0 = unit_wave_vector_fast(kx.x, ky);
+            const float2 k_1 = unit_wave_vector_fast(kx.y, ky);
+            F4[i] = make_float4(h_0.x, h_0.y, h_1.x, h_1.y);                 // H[x], H[x + 1]
+            R4[N / 2 - 1 - i] = make_float4(k_1.x, k_1.y, k_0.x, k_0.y);     // K[x + 1] at REV[N-2-x], K[x] at REV[N-1-x]
+            if (i == 0) {
+                sl.fwd()[N] = h_0;                                           // H[N] = H[0]
+                sl.rev()[-1] = k_0;                                          // K[N] = K[0] (the spare slot before REV)
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: three line transforms per row pair
+    const int f = tid / T;                // line index in the block
+    const int pair = f / 3, seq = f % 3;
+    const int k2 = tid % T;
+    const uint32_t j = blockIdx.x * PAIRS + pair;
+    const bool self_paired = (j == 0);
+    const Slot S0{smem_raw + (2 * pair) * Slot::BYTES}, S1{smem_raw + (2 * pair + 1) * Slot::BYTES};
+    float2* line = X + f * Cfg::LINE;
+
+    float2 v[R1];
+    if (seq < 2) {
+        // as in k_rows: seq 0: A = (x, y), B = (-x, N-y); seq 1: A = (-x, N-y), B = (x, y); rows 0 and N/2: A = (x, r), B = (-x, r)
+        const bool mirror_a = !self_paired && seq == 1;
+        const Slot PA = (seq == 0) ? S0 : S1;
+        const Slot PB = self_paired ? PA : (seq == 0 ? S1 : S0);
+        const int step = mirror_a ? -T : T;
+        const int ia = mirror_a ? N - k2 : k2, ib = mirror_a ? k2 : N - k2;
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            const float2 qa = rot_mul(PA.rec(ia + k1 * step)), qb = rot_mul_conj(PB.rec(ib - k1 * step));
+            v[k1] = make_float2(qa.x - qb.x, qa.y - qb.y);
+        }
+    } else if (!self_paired) {
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            const float2 A = S0.h(k2 + k1 * T), B = S1.h(N - k2 - k1 * T);
+            v[k1] = make_float2(A.x + B.x, A.y - B.y);
+        }
+    } else {
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            const int x = k1 * T + k2;
+            const float2 a0 = S0.h(x), b0 = S0.h(N - x), a1 = S1.h(x), b1 = S1.h(N - x);
+            v[k1] = make_float2((a0.x + b0.x) - (a1.y - b1.y), (a0.y - b0.y) + (a1.x + b1.x));
+        }
+    }
+    __syncthreads();                      // every warp has its inputs: the slots may be overwritten by the lines
+    rows_line_finish<N, P, C>(v, line, k2, seq, j, tw_g, gp, gh);
+}
+
+// ------------------------------------------------------------------------------------------
 // k_rows_p: persistent, bulk-copy fed k_rows with the Hermitian fold done at the source
 // ------------------------------------------------------------------------------------------
 // One CTA per SM: GROUPS independent groups of 3*PAIRS*T threads plus (SLOTS > 0) one producer warp. A group takes
@@ -377,20 +560,25 @@ __device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1
 #ifndef OCEAN_ROWS_UNROLL
 #define OCEAN_ROWS_UNROLL 4
 #endif
+#ifndef OCEAN_ROWS_PF_OP
+#define OCEAN_ROWS_PF_OP "prefetch.global.L2"
+#endif
 template <int N, int P, int PAIRS, int C, int GROUPS, int SLOTS>
 struct RowsCfg {
     using Line = LineCfg<N, P>;
     static constexpr int T = Line::T;
     static constexpr int LINES = 3 * PAIRS;               // lines per group
     static constexpr int GT = LINES * T;                  // threads per group
-    static constexpr int NTHREADS = GROUPS * GT + (SLOTS > 0 ? 32 : 0);
+    static constexpr int RING = SLOTS > 0 ? SLOTS : 0;    // SLOTS > 0: bulk-copy ring; SLOTS < 0: L2 prefetch warp, -SLOTS units ahead
+    static constexpr int AHEAD = SLOTS < 0 ? -SLOTS : 0;
+    static constexpr int NTHREADS = GROUPS * GT + (SLOTS != 0 ? 32 : 0);
     static constexpr int UPT = N / 2 / PAIRS;             // units per tile
     static constexpr size_t GROUP_SMEM = sizeof(float2) * LINES * Line::LINE;
     static constexpr size_t LINES_SMEM = GROUPS * GROUP_SMEM;
     // raw rows of one row pair: h0 rows [F0][P0][F1][P1], omega rows [W0][W1]
     static constexpr uint32_t PAIR_RAW = 4 * N * sizeof(float2) + 2 * N * sizeof(float);
     static constexpr uint32_t SLOT_BYTES = PAIRS * PAIR_RAW;
-    static constexpr size_t SMEM = LINES_SMEM + size_t(SLOTS) * SLOT_BYTES + (SLOTS > 0 ? 2 * SLOTS * sizeof(uint64_t) : 0);
+    static constexpr size_t SMEM = LINES_SMEM + size_t(RING) * SLOT_BYTES + (RING > 0 ? 2 * RING * sizeof(uint64_t) : 0);
     static_assert(GT % 32 == 0 && GROUPS >= 1 && GROUPS <= 15, "groups synchronise on named barriers 1..GROUPS");
     static_assert(LINES_SMEM % 16 == 0 && PAIR_RAW % 16 == 0, "bulk copies need 16-byte granules");
 };
@@ -487,8 +675,11 @@ __device__ __forceinline__ void fold_pair(uint32_t jp, const float2* F0, const f
 
 // (ptxas sizes registers for the thread count rounded up to whole groups of four warps: each of the SM's four
 // sub-partitions has its own 16 K-register file, so 15 warps cost what 16 do -- the producer warp is free)
+#ifndef OCEAN_ROWS_FOLD_MINB
+#define OCEAN_ROWS_FOLD_MINB 5
+#endif
 template <int N, int P, int PAIRS, int C, int GROUPS, int SLOTS>
-__global__ void __launch_bounds__(RowsCfg<N, P, PAIRS, C, GROUPS, SLOTS>::NTHREADS, 1)
+__global__ void __launch_bounds__(RowsCfg<N, P, PAIRS, C, GROUPS, SLOTS>::NTHREADS, GROUPS == 1 ? OCEAN_ROWS_FOLD_MINB : 1)
 k_rows_p(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, const float2* __restrict__ tw_g,
          const float* __restrict__ kx_g, float2* __restrict__ gp_all, float2* __restrict__ gh_all, float time,
          uint32_t first_tile, uint32_t n_units)
@@ -503,8 +694,8 @@ k_rows_p(const float2* __restrict__ h0_all, const float* __restrict__ omega_all,
     __shared__ uint32_t s_unit[2][GROUPS];   // the group's next unit, double-buffered by iteration parity
     __shared__ uint32_t s_done[SLOTS > 0 ? SLOTS : 1];   // units whose phase A has drained each raw slot (monotonic)
     unsigned char* raw_base = smem_raw + RC::LINES_SMEM;
-    uint64_t* full = reinterpret_cast<uint64_t*>(raw_base + size_t(SLOTS) * RC::SLOT_BYTES);   // [SLOTS] raw rows landed (tx bytes)
-    uint64_t* empty = full + SLOTS;                                                             // [SLOTS] phase A done (GT arrivals)
+    uint64_t* full = reinterpret_cast<uint64_t*>(raw_base + size_t(RC::RING) * RC::SLOT_BYTES);   // [RING] raw rows landed (tx bytes)
+    uint64_t* empty = full + RC::RING;                                                             // [RING] phase A done (GT arrivals)
 
     const int tid = threadIdx.x;
     pdl_launch_dependents();
@@ -523,6 +714,39 @@ k_rows_p(const float2* __restrict__ h0_all, const float* __restrict__ omega_all,
     }
     __syncthreads();
 
+    if constexpr (SLOTS < 0) {
+        if (tid >= GROUPS * GT) {
+            // ================= prefetch warp =================
+            // Pulls the raw rows of the units the groups will take next from DRAM into L2 (prefetch.global.L2), a few
+            // units ahead of the ticket counter, so phase A's loads are L2 hits. No shared memory, no registers of the
+            // compute warps, and nothing to wait for: a late prefetch only costs the latency it failed to hide.
+            const uint32_t lane = tid & 31;
+            uint32_t done = u_begin + GROUPS;
+            while (done < u_end) {
+                const uint32_t next = *reinterpret_cast<volatile uint32_t*>(&s_next);
+                if (done < next + RC::AHEAD) {
+                    const uint32_t tl = done / RC::UPT, bx = done % RC::UPT;
+                    const char* h0 = reinterpret_cast<const char*>(h0_all + size_t(first_tile + tl) * N * N);
+                    const char* om = reinterpret_cast<const char*>(omega_all + size_t(first_tile + tl) * N * N);
+#pragma unroll 1
+                    for (int p = 0; p < PAIRS; ++p) {
+                        uint32_t hr[4], wr[2];
+                        pair_rows<N>(bx * PAIRS + p, hr, wr);
+                        for (int i = 0; i < 4; ++i)
+                            for (uint32_t o = lane * 128; o < N * sizeof(float2); o += 32 * 128)
+                                asm volatile(OCEAN_ROWS_PF_OP " [%0];" ::"l"(h0 + size_t(hr[i]) * N * sizeof(float2) + o));
+                        for (int i = 0; i < 2; ++i)
+                            for (uint32_t o = lane * 128; o < N * sizeof(float); o += 32 * 128)
+                                asm volatile(OCEAN_ROWS_PF_OP " [%0];" ::"l"(om + size_t(wr[i]) * N * sizeof(float) + o));
+                    }
+                    ++done;
+                } else {
+                    __nanosleep(256);
+                }
+            }
+            return;
+        }
+    }
     if constexpr (SLOTS > 0) {
         if (tid >= GROUPS * GT) {
             // ================= producer warp =================
@@ -979,7 +1203,10 @@ struct FusedPlan {
     int cols_blocks_per_sm = 1;  // persistent k_cols blocks resident per SM
     int rows_blocks_per_sm = 1;  // k_rows blocks resident per SM (occupancy)
     int pdl_mode = -1;           // programmatic dependent launch: -1 auto, 0 off, 1 on (env OCEAN_B200_PDL)
-    int rows_legacy = 0;         // 1: round-1 k_rows (one block per row pair) for A/B runs (env OCEAN_B200_ROWS=legacy)
+    // which row kernel (env OCEAN_B200_ROWS): 3 "tma" (default) = k_rows_t; 0 "staged" = k_rows; 1 "persistent" = k_rows_p
+    // with its bulk-copy-fed ring; 2 "fold" = k_rows_p with one unit per block. Measured on B200 at N = 1024 x 8 tiles,
+    // whole step: 99 / 107 / 113-131 / 118 us.
+    int rows_mode = 3;
     float2* d_tw = nullptr;      // [R1][R2] inter-pass twiddles
     float* d_kx = nullptr;       // [N] wave numbers, propagate.comp:45-46,50-53
     float2* d_gp = nullptr;      // [tiles] strip-major packed (dx, dz) row-pass output
@@ -993,6 +1220,8 @@ struct Launch {
     using CC = ColsCfg<N, P, C>;
     using IL = typename CC::IL;
     using RC = RowsCfg<N, P, PPAIRS, C, GROUPS, SLOTS>;
+    using RC1 = RowsCfg<N, P, PPAIRS, C, 1, 0>;            // one unit per block, hardware-scheduled
+    static constexpr size_t smem_rows_t = size_t(2 * PAIRS) * RowSlot<N>::BYTES + 16;
     static constexpr size_t smem_rows = sizeof(float4) * 2 * PAIRS * (N + 1);
 
     static cudaError_t prepare(FusedPlan* p)
@@ -1000,6 +1229,10 @@ struct Launch {
         cudaError_t e = cudaFuncSetAttribute(k_rows<N, P, PAIRS, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_rows));
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_rows_p<N, P, PPAIRS, C, GROUPS, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(RC::SMEM));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_rows_p<N, P, PPAIRS, C, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(RC1::SMEM));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_rows_t<N, P, PAIRS, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_rows_t));
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_cols<N, P, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(CC::SMEM));
         if (e != cudaSuccess) return e;
@@ -1035,7 +1268,14 @@ struct Launch {
         const bool skip_rows = debug_env && std::getenv("OCEAN_B200_DEBUG_SKIP_ROWS") != nullptr;   // re-run k_cols on the same intermediate
         if (skip_rows) {
             e = cudaSuccess;
-        } else if (p->rows_legacy) {
+        } else if (p->rows_mode == 3) {
+            // staged rows fed by bulk copies: every storing block waits on the prior grid itself, PDL is safe at any size
+            attr[0].val.programmaticStreamSerializationAllowed = p->pdl_mode == 0 ? 0 : 1;
+            cfg.gridDim = dim3(N / 2 / PAIRS, count);
+            cfg.blockDim = dim3(3 * PAIRS * Cfg::T);
+            cfg.dynamicSmemBytes = smem_rows_t;
+            e = cudaLaunchKernelEx(&cfg, k_rows_t<N, P, PAIRS, C, MINB>, h0, omega, tw, kx, gp, gh, time, first_tile);
+        } else if (p->rows_mode == 0) {
             // measured on B200 (N=1024): PDL gains 21% / 7% at 1 / 4 tiles per launch (it hides ramp and tail) and
             // loses 1.5-3.5% at 8-16 tiles, so it is used while the row grid is below four waves
             const bool pdl = p->pdl_mode == 1 || (p->pdl_mode < 0 && (N / 2 / PAIRS) * count < 4u * uint32_t(p->num_sms) * MINB);
@@ -1045,6 +1285,14 @@ struct Launch {
             cfg.dynamicSmemBytes = smem_rows;
             const uint32_t resident = uint32_t(p->num_sms * p->rows_blocks_per_sm);
             e = cudaLaunchKernelEx(&cfg, k_rows<N, P, PAIRS, C, MINB>, h0, omega, tw, kx, gp, gh, time, first_tile, resident);
+        } else if (p->rows_mode == 2) {
+            // fold-at-source kernel, one unit per block (no tickets): the hardware block scheduler does the balancing
+            attr[0].val.programmaticStreamSerializationAllowed = p->pdl_mode == 0 ? 0 : 1;
+            const uint32_t units = count * uint32_t(RC1::UPT);
+            cfg.gridDim = dim3(units);
+            cfg.blockDim = dim3(RC1::NTHREADS);
+            cfg.dynamicSmemBytes = RC1::SMEM;
+            e = cudaLaunchKernelEx(&cfg, k_rows_p<N, P, PPAIRS, C, 1, 0>, h0, omega, tw, kx, gp, gh, time, first_tile, units);
         } else {
             // persistent rows: every storing thread waits on the prior grid itself, so PDL is safe at any size
             attr[0].val.programmaticStreamSerializationAllowed = p->pdl_mode == 0 ? 0 : 1;
@@ -1144,7 +1392,7 @@ cudaError_t fused_plan_create(FusedPlan** out, uint32_t n, uint32_t n_tiles, flo
     p->n_tiles = n_tiles;
     p->domain_size = domain_size;
     if (const char* v = std::getenv("OCEAN_B200_PDL")) p->pdl_mode = v[0] == '1' ? 1 : (v[0] == '0' ? 0 : -1);
-    if (const char* v = std::getenv("OCEAN_B200_ROWS")) p->rows_legacy = v[0] == 'l' ? 1 : 0;
+    if (const char* v = std::getenv("OCEAN_B200_ROWS")) p->rows_mode = v[0] == 'p' ? 1 : (v[0] == 'f' ? 2 : (v[0] == 's' ? 0 : 3));
     cudaError_t e;
     auto bail = [&](cudaError_t err) { fused_plan_destroy(p); return err; };
     if ((e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail(e);

@@ -411,10 +411,17 @@ int enqueue_frame(ocean_ctx* c, float time, uint32_t first_tile, uint32_t count,
             }
         }
     } else {
-        uint32_t nl = 0;
-        OCEAN_CUDA(c, ocean::fused_enqueue(c->plan, c->d_h0, c->d_omega, c->d_out_tab[c->cur], time, first_tile, count, c->stream,
-                                           &nl, ev, c->any_pitched || sums != nullptr, sums));
-        c->launches += nl;
+        // tiles per kernel pair: the whole range by default; OCEAN_B200_BATCH=k splits it so that a batch's row-pass
+        // output is still in L2 when its column pass reads it (experiment knob)
+        static const uint32_t batch_env = [] { const char* v = std::getenv("OCEAN_B200_BATCH"); return v ? uint32_t(std::atoi(v)) : 0u; }();
+        const uint32_t batch = (batch_env && !ev) ? batch_env : count;
+        for (uint32_t t0 = first_tile; t0 < first_tile + count; t0 += batch) {
+            const uint32_t cnt = t0 + batch <= first_tile + count ? batch : first_tile + count - t0;
+            uint32_t nl = 0;
+            OCEAN_CUDA(c, ocean::fused_enqueue(c->plan, c->d_h0, c->d_omega, c->d_out_tab[c->cur], time, t0, cnt, c->stream,
+                                               &nl, ev, c->any_pitched || sums != nullptr, sums ? sums + (t0 - first_tile) : nullptr));
+            c->launches += nl;
+        }
     }
     if (c->n_buffers == 2) OCEAN_CUDA(c, cudaEventRecord(c->ev_done[c->cur], c->stream));
     c->updated = true;

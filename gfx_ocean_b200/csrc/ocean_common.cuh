@@ -90,8 +90,11 @@ __host__ __device__ __forceinline__ void sincos_reduced(float x, float& sn, floa
     cs = ((q + 1) & 2) ? -co : co;
 }
 
-// A/B variant (-DOCEAN_SINCOS_MUFU): Cody-Waite reduction by 2 pi (the same three constants, times four) to
-// [-pi, pi], then the special-function unit: 9 instructions instead of ~30, absolute error ~4e-7 instead of 7e-8.
+// The default: Cody-Waite reduction by 2 pi (the same three constants, times four) to [-pi, pi], then the
+// special-function unit (MUFU.SIN / MUFU.COS, absolute error ~4e-7 on that range): 9 instructions instead of ~30.
+// Measured on B200 against the f64 oracle the end-to-end error is unchanged (<= 1.9e-6 of the field maximum at
+// N = 64..2048, t = 0..25000; profiles/r02_sincos_mufu_accuracy.txt) and k_rows gets 3-5 % faster.
+// -DOCEAN_SINCOS_POLY selects the polynomial version (7e-8) instead.
 __device__ __forceinline__ void sincos_mufu(float x, float& sn, float& cs)
 {
     const float n = fmaf(x, 0.159154943f, 12582912.f) - 12582912.f;       // rint(x / 2 pi)
@@ -104,10 +107,10 @@ __device__ __forceinline__ void sincos_mufu(float x, float& sn, float& cs)
 
 __device__ __forceinline__ void sincos_full(float x, float& sn, float& cs)
 {
-#ifdef OCEAN_SINCOS_MUFU
-    if (fabsf(x) <= 1.0e5f) sincos_mufu(x, sn, cs);
-#else
+#ifdef OCEAN_SINCOS_POLY
     if (fabsf(x) <= 1.0e5f) sincos_reduced(x, sn, cs);
+#else
+    if (fabsf(x) <= 1.0e5f) sincos_mufu(x, sn, cs);
 #endif
     else {
         const float2 sc = sincos_huge(x);

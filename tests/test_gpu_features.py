@@ -55,11 +55,13 @@ def test_benchmarked_configuration_every_tile_matches_oracle(oracle):
 def test_every_frame_is_bit_identical_with_and_without_pdl(n, tiles, frames):
     """The hazard programmatic dependent launch could open: k_rows of frame n+1 overwriting the intermediate while
     k_cols of frame n still reads it. The column kernel checksums what it stores, for EVERY frame of a back-to-back
-    sequence; PDL on, PDL off and the round-1 row kernel must agree bit for bit."""
+    sequence; PDL on and PDL off must agree bit for bit, for the default row kernel and for its alternatives."""
     data = [synthetic_tile(n, g) for g in range(tiles)]
     sums = {}
     for name, kv in (("pdl1", dict(OCEAN_B200_PDL="1")), ("pdl0", dict(OCEAN_B200_PDL="0")),
-                     ("legacy_pdl0", dict(OCEAN_B200_PDL="0", OCEAN_B200_ROWS="legacy"))):
+                     ("staged_pdl1", dict(OCEAN_B200_PDL="1", OCEAN_B200_ROWS="staged")),
+                     ("persistent_pdl1", dict(OCEAN_B200_PDL="1", OCEAN_B200_ROWS="persistent")),
+                     ("fold_pdl0", dict(OCEAN_B200_PDL="0", OCEAN_B200_ROWS="fold"))):
         with env(**kv):
             with Ocean(n, 1000.0, n_tiles=tiles) as o:
                 for i, (h0, w) in enumerate(data):
@@ -68,19 +70,25 @@ def test_every_frame_is_bit_identical_with_and_without_pdl(n, tiles, frames):
                 last = o.output_checksums()
         np.testing.assert_array_equal(sums[name][-1], last)       # in-kernel checksum == reduction kernel's
     np.testing.assert_array_equal(sums["pdl1"], sums["pdl0"])
+    np.testing.assert_array_equal(sums["pdl1"], sums["staged_pdl1"])             # bulk-copy fed vs register-staged loads
+    np.testing.assert_array_equal(sums["persistent_pdl1"], sums["fold_pdl0"])   # same arithmetic, two launch structures
     assert len(np.unique(sums["pdl0"][:, 0])) == frames            # the frames do differ from each other
 
 
-def test_legacy_and_persistent_rows_agree_closely(oracle):
-    """Different summation order in the fold (fold-at-source vs per-line), same result to rounding."""
-    h0, w = synthetic_tile(1024, 5)
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048])
+def test_row_kernel_variants_agree_closely(n, oracle):
+    """Staged rows (default, bulk-copy fed) vs fold at the source (persistent bulk-copy-fed / one unit per block):
+    different summation order in the fold, same result to rounding; the two fold variants are bit-identical."""
+    h0, w = synthetic_tile(n, 5)
     outs = []
-    for kv in (dict(OCEAN_B200_ROWS=None), dict(OCEAN_B200_ROWS="legacy")):
+    for kv in (dict(OCEAN_B200_ROWS="tma"), dict(OCEAN_B200_ROWS="persistent"), dict(OCEAN_B200_ROWS="fold")):
         with env(**kv):
-            with Ocean.new(1024, 1000.0, w, h0) as o:
+            with Ocean.new(n, 1000.0, w, h0) as o:
                 o.update(3.0)
                 outs.append(o.read_back())
     assert max(max_rel_err(outs[0], outs[1])) <= 2e-6
+    np.testing.assert_array_equal(outs[1], outs[2])
+    assert max(max_rel_err(outs[1], oracle.frame(h0, w, 3.0, n, prec="f64"))) <= TOL
 
 
 def test_tile_results_do_not_depend_on_batching_or_slot():
