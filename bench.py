@@ -504,7 +504,9 @@ def main():
                                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                                 "alg_bytes_per_launch": alg[d], "launch_ms": stage_ms[d],
                                 "launch_ms_clock": "CUDA events recorded between the launches on the launching stream "
-                                                   "(ocean_profile_update, median of 30 frames); includes the inter-kernel gap",
+                                                   "(ocean_profile_update, median of 30 frames); includes the inter-kernel gap. The event "
+                                                   "between the kernels serialises them, so the two durations add up to MORE than ms_per_step: in "
+                                                   "the timed loop programmatic dependent launch overlaps the head of k_rows with the tail of k_cols",
                                 "real_bytes_per_launch": real[d], "real_bytes_frac": real[d] / (stage_ms[d] * 1e-3) / 1e9 / peak,
                                 "traffic_frac": (traffic / (stage_ms[d] * 1e-3) / 1e9 / peak) if traffic else None,
                                 "traffic_source": "profiles/traffic.json (ncu --set full capture of the same kernel, per launch)"}

@@ -480,8 +480,9 @@ k_rows_t(const float2* __restrict__ h0_all, const float* __restrict__ omega_all,
         const float2* __restrict__ pk = reinterpret_cast<const float2*>(kx_g);
 #pragma unroll 2
         for (int i = tid; i < N / 2; i += NT) {
+            const float2 w = W2[i];
             const float4 a = F4[i], b = R4[N / 2 - 1 - i];     // b.zw is the partner of x = 2 i, b.xy the partner of x + 1
-            const float2 w = W2[i], kx = __ldg(pk + i);
+            const float2 kx = __ldg(pk + i);
             const float2 h_0 = propagate_point_fast(make_float2(a.x, a.y), make_float2(b.z, b.w), w.x, time);
             const float2 h_1 = propagate_point_fast(make_float2(a.z, a.w), make_float2(b.x, b.y), w.y, time);
             const float2 k_0 = unit_wave_vector_fast(kx.x, ky);
@@ -1099,6 +1100,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
             const uint32_t tl = item / STRIPS, n0 = (item % STRIPS) * C;
             const uint32_t b = it & 1;
             float2* PB = b ? PB1 : PB0;
+            const OutDesc od = out_tab[first_tile + tl];          // in flight while the strip lands
             ptx::mbar_wait(fullP + b, (it >> 1) & 1);
             float2 v[R1];
             // position p = k1 T + k2 lives at row_off(p) + c; T is a multiple of the group size, so k1 strides whole groups
@@ -1111,7 +1113,6 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
             for (int n1 = 0; n1 < R1; ++n1)
                 col[n1 * K1_STRIDE] = n1 == 0 ? v[0] : cmul_tw(v[n1], TW[n1 * T + k2]);
             ptx::named_bar_sync<1, NTP>();
-            const OutDesc od = out_tab[first_tile + tl];
             float4* __restrict__ out = od.base + n0 + c;
             const size_t pitch = GENERAL ? size_t(od.pitch) : size_t(N);
             unsigned long long csum = 0;
