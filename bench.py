@@ -211,7 +211,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from gfx_ocean_b200 import FLAG_DOUBLE_BUFFER_OUTPUT, Ocean, PIPELINE_FUSED, PIPELINE_LITERAL
+    from gfx_ocean_b200 import FLAG_DOUBLE_BUFFER_OUTPUT, FLAG_DX_PLANE, Ocean, PIPELINE_FUSED, PIPELINE_LITERAL
     from gfx_ocean_b200.shard import tiles_of_rank
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -354,19 +354,30 @@ def main():
             acc.append(ocean.profile_update(args.dt * i))
         stage_ms = np.median(np.array(acc), axis=0).tolist()
 
-    # ---- consumer step: frames/s with the normal map of ocean.frag:50-66 computed after every frame
+    # ---- consumer step: frames/s with the normal map of ocean.frag:50-66 computed after every frame; (i) gathered from
+    #      the RGBA texels, (ii) on a context whose column kernel also writes a dense copy of channel .x
     with_normals = None
     if extras:
-        with torch.cuda.stream(stream):
-            for i in range(3):
-                ocean.update(args.dt * i)
-                ocean.compute_normals()
-            kn = max(50, K // 10)
-            rn = repeated(lambda i: (ocean.update(args.dt * i), ocean.compute_normals()), kn, 5, 0.2)
-        mn = statistics.median(rn)
-        with_normals = {"value": tiles * kn / (mn * 1e-3), "unit": UNIT, "ms_per_step": mn / kn,
-                        "normal_map_ms_per_step": mn / kn - ms / K,
-                        "note": "ocean_update + ocean_compute_normals (separate kernel: 16 B/pt read + 16 B/pt written)"}
+        kn = max(50, K // 10)
+
+        def normals_rate(o):
+            with torch.cuda.stream(stream):
+                for i in range(3):
+                    o.update(args.dt * i)
+                    o.compute_normals()
+                rn = repeated(lambda i: (o.update(args.dt * i), o.compute_normals()), kn, 5, 0.2)
+            return statistics.median(rn)
+        mn = normals_rate(ocean)
+        with Ocean(n, 1000.0, n_tiles=tiles, device=local_rank, stream=stream.cuda_stream, flags=FLAG_DX_PLANE) as on:
+            for i, g in enumerate(my_tiles):
+                on.generate_spectrum(i, SEED, stream_id=g)
+            mp = normals_rate(on)
+        with_normals = {"value": tiles * kn / (mp * 1e-3), "unit": UNIT, "ms_per_step": mp / kn,
+                        "normal_map_ms_per_step": mp / kn - ms / K,
+                        "from_rgba_texels": {"value": tiles * kn / (mn * 1e-3), "ms_per_step": mn / kn},
+                        "note": "ocean_update + ocean_compute_normals every frame. value: OCEAN_FLAG_DX_PLANE context (k_cols "
+                                "also writes channel .x densely, +4 B/pt; the normal kernel reads 4 + writes 16 B/pt); "
+                                "from_rgba_texels: the normal kernel gathers .x out of the RGBA map (16 + 16 B/pt)"}
 
     # ---- library sanity bar: cuFFT's batched 2-D C2C inverse transform ALONE on the same
     #      amount of data (3 complex fields per tile, via torch.fft.ifft2), without propagate or correction.

@@ -53,6 +53,7 @@ pub const OCEAN_PIPELINE_FUSED: u32 = 0;
 pub const OCEAN_PIPELINE_LITERAL: u32 = 1;
 pub const OCEAN_FLAG_KEEP_SPECTRA: u32 = 1;
 pub const OCEAN_FLAG_DOUBLE_BUFFER_OUTPUT: u32 = 2;
+pub const OCEAN_FLAG_DX_PLANE: u32 = 4;
 
 /// Parameters of `ocean_generate_spectrum` (NULL: amplitude 3e-8, wind 30 m/s, g 9.81, depth 100 m).
 #[repr(C)]

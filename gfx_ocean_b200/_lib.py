@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("OCEAN_B200_LIB") or os.path.join(HERE, "libocean_b200
 ABI_VERSION = 2
 OK, ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_IO, ERR_NOT_READY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 PIPELINE_FUSED, PIPELINE_LITERAL = 0, 1
-FLAG_KEEP_SPECTRA, FLAG_DOUBLE_BUFFER_OUTPUT = 1, 2
+FLAG_KEEP_SPECTRA, FLAG_DOUBLE_BUFFER_OUTPUT, FLAG_DX_PLANE = 1, 2, 4
 
 
 class PropagateLocals(C.Structure):

@@ -20,6 +20,8 @@ bool literal_supports(uint32_t n);
 // shader/ocean.frag:50-66 at texel centres; nrm: dense [tiles][N][N] float4
 cudaError_t launch_normal_map(const float4* disp, size_t disp_pitch, size_t disp_tile_stride, float4* nrm, uint32_t n,
                               uint32_t tiles, cudaStream_t s);
+// same from the dense copy of channel .x that k_cols can write (float[tiles][N][N])
+cudaError_t launch_normal_map_plane(const float* dx_plane, float4* nrm, uint32_t n, uint32_t tiles, cudaStream_t s);
 // shader/ocean.vert:21-25,29 for a grid x grid vertex patch; pos_world: [grid*grid][3]
 cudaError_t launch_displace_grid(const float4* disp, size_t pitch, uint32_t n, uint32_t grid, float off_x, float off_z,
                                  float* pos_world, cudaStream_t s);
@@ -44,10 +46,12 @@ struct OutDesc {
 };
 // Enqueue one frame for tiles [first_tile, first_tile + count); *launches = kernels launched.
 // out_tab: device array of OutDesc indexed by tile; `general` selects the k_cols build that honours row pitches
-// != N and (checksums != nullptr) adds every tile's output checksum into checksums[tile - first_tile].
+// != N and (checksums != nullptr) adds every tile's output checksum into checksums[tile - first_tile];
+// dx_plane (optional): dense float[tile][y][x] copy of channel .x for the normal-map kernel.
 // If `ev` is non-null it holds 3 events recorded before, between and after the two kernels.
 cudaError_t fused_enqueue(FusedPlan* p, const float2* h0, const float* omega, const OutDesc* out_tab, float time,
                           uint32_t first_tile, uint32_t count, cudaStream_t s, uint32_t* launches,
-                          cudaEvent_t* ev = nullptr, bool general = false, unsigned long long* checksums = nullptr);
+                          cudaEvent_t* ev = nullptr, bool general = false, unsigned long long* checksums = nullptr,
+                          float* dx_plane = nullptr);
 
 }  // namespace ocean

@@ -17,16 +17,20 @@ namespace ocean {
 // exactly the wrapped neighbour texel.
 constexpr int kNormalRows = 16;
 
+// ocean.frag:64-66: na = normalize(-diff, (x1-x0)/height_scale, 0), nb = normalize(0, (z1-z0)/height_scale, diff),
+// N = normalize(cross(na, nb)). cross(na, nb) = (dxv diff, diff^2, -diff dzv) / (|na| |nb|) with dxv, dzv the two
+// scaled differences, and the positive factor diff / (|na| |nb|) drops out of the final normalisation:
+// N = (dxv, diff, -dzv) / sqrt(dxv^2 + diff^2 + dzv^2) -- one reciprocal square root instead of three square roots
+// and nine divisions (the literal form made this kernel ALU bound: ~150 instructions per texel).
 __device__ __forceinline__ float4 normal_from_differences(float x0, float x1, float z0, float z1, float diff)
 {
-    const float height_scale = 180.0f;                                  // ocean.frag:19
-    float nax = -diff, nay = (x1 - x0) / height_scale;                  // :64
-    float nby = (z1 - z0) / height_scale, nbz = diff;                   // :65
-    const float la = sqrtf(nax * nax + nay * nay), lb = sqrtf(nby * nby + nbz * nbz);
-    nax /= la; nay /= la; nby /= lb; nbz /= lb;
-    const float cx = nay * nbz, cy = -nax * nbz, cz = nax * nby;        // :66 cross(na, nb)
-    const float lc = sqrtf(cx * cx + cy * cy + cz * cz);
-    return make_float4(cx / lc, cy / lc, cz / lc, 0.0f);
+    const float inv_height_scale = 1.0f / 180.0f;                       // ocean.frag:19
+    const float dxv = (x1 - x0) * inv_height_scale, dzv = (z1 - z0) * inv_height_scale;
+    const float l2 = fmaf(dxv, dxv, fmaf(dzv, dzv, diff * diff));
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l2));           // l2 >= diff^2 > 0
+    r = r * fmaf(-0.5f * l2, r * r, 1.5f);                              // one Newton step: ~1e-7 relative
+    return make_float4(dxv * r, diff * r, -dzv * r, 0.0f);
 }
 
 __global__ void __launch_bounds__(256)
@@ -54,6 +58,41 @@ k_normal_map(const float4* __restrict__ disp, size_t disp_pitch, size_t disp_til
         up = cur;
         cur = down;
     }
+}
+
+// The same walk over the dense channel-.x plane k_cols writes on request: 4 B per texel read instead of 16.
+__global__ void __launch_bounds__(256)
+k_normal_map_plane(const float* __restrict__ dxp, float4* __restrict__ nrm, uint32_t n)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t x = (blockIdx.x * (blockDim.x >> 5) + warp) * 32 + lane;
+    if (x - lane >= n) return;
+    const uint32_t m = n - 1;
+    const float* __restrict__ d = dxp + size_t(blockIdx.z) * n * n;
+    float4* __restrict__ o = nrm + size_t(blockIdx.z) * n * n;
+    const uint32_t y0 = blockIdx.y * kNormalRows;
+    const float diff = 2.0f / float(n);
+    const uint32_t xl = (x - 1) & m, xr = (x + 1) & m;
+    float up = __ldg(&d[x + size_t(n) * ((y0 - 1) & m)]);
+    float cur = __ldg(&d[x + size_t(n) * y0]);
+#pragma unroll 4
+    for (uint32_t r = 0; r < kNormalRows; ++r) {
+        const uint32_t y = y0 + r;
+        const float down = __ldg(&d[x + size_t(n) * ((y + 1) & m)]);
+        float x0 = __shfl_up_sync(0xffffffffu, cur, 1), x1 = __shfl_down_sync(0xffffffffu, cur, 1);
+        if (lane == 0) x0 = __ldg(&d[xl + size_t(n) * y]);
+        if (lane == 31) x1 = __ldg(&d[xr + size_t(n) * y]);
+        __stcs(&o[x + size_t(n) * y], normal_from_differences(x0, x1, up, down, diff));
+        up = cur;
+        cur = down;
+    }
+}
+
+cudaError_t launch_normal_map_plane(const float* dx_plane, float4* nrm, uint32_t n, uint32_t tiles, cudaStream_t s)
+{
+    if (n < 32 || n % kNormalRows) return cudaErrorInvalidValue;
+    k_normal_map_plane<<<dim3((n + 255) / 256, n / kNormalRows, tiles), n < 256 ? n : 256, 0, s>>>(dx_plane, nrm, n);
+    return cudaGetLastError();
 }
 
 // small grids (n < 32): one thread per texel

@@ -405,7 +405,8 @@ struct RowSlot {
 template <int N, int P, int PAIRS, int C, int MINB>
 __global__ void __launch_bounds__(3 * PAIRS * (N / P), MINB)
 k_rows_t(const float2* __restrict__ h0_all, const float* __restrict__ omega_all, const float2* __restrict__ tw_g,
-         const float* __restrict__ kx_g, float2* __restrict__ gp_all, float2* __restrict__ gh_all, float time, uint32_t first_tile)
+         const float* __restrict__ kx_g, float2* __restrict__ gp_all, float2* __restrict__ gh_all, float time, uint32_t first_tile,
+         uint32_t /*keeps the parameter list of all row kernels alike: ocean_update_graph patches `time` by position*/)
 {
     using Cfg = LineCfg<N, P>;
     using Slot = RowSlot<N>;
@@ -933,7 +934,8 @@ struct ColsCfg {
 template <int N, int P, int C, bool GENERAL>
 __global__ void __launch_bounds__(ColsCfg<N, P, C>::NTHREADS, 1)
 k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, const float2* __restrict__ tw_g,
-       const OutDesc* __restrict__ out_tab, uint32_t first_tile, uint32_t n_items, unsigned long long* __restrict__ checksums)
+       const OutDesc* __restrict__ out_tab, uint32_t first_tile, uint32_t n_items, unsigned long long* __restrict__ checksums,
+       float* __restrict__ dx_plane)
 {
     using CC = ColsCfg<N, P, C>;
     using Cfg = typename CC::Line;
@@ -1115,12 +1117,16 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
             ptx::named_bar_sync<1, NTP>();
             float4* __restrict__ out = od.base + n0 + c;
             const size_t pitch = GENERAL ? size_t(od.pitch) : size_t(N);
+            // optional dense copy of channel .x (what the normal map differentiates, ocean.frag:56-59): 4 B/pt here save
+            // the consumer kernel 12 of the 16 B/pt it would otherwise fetch
+            float* __restrict__ dxp = dx_plane ? dx_plane + size_t(first_tile + tl) * N * N + n0 + c : nullptr;
             unsigned long long csum = 0;
             auto emit = [&](uint32_t m, float dx, float hh, float dz) {
                 // correction.comp:29 sign, times the 1/2 of the Hermitian fold
                 const float sg = ((n0 + c + m) & 1u) ? 0.5f : -0.5f;
                 const float4 t = make_float4(dx * sg, hh * sg, dz * sg, 0.0f);
                 __stcs(out + size_t(m) * pitch, t);
+                if (dxp) dxp[size_t(m) * N] = t.x;
                 if constexpr (GENERAL)
                     csum += (unsigned long long)__float_as_uint(t.x) + __float_as_uint(t.y) * 3ull + __float_as_uint(t.z) * 5ull;
             };
@@ -1252,7 +1258,7 @@ struct Launch {
 
     static cudaError_t run(FusedPlan* p, const float2* h0, const float* omega, const OutDesc* out, float time,
                            uint32_t first_tile, uint32_t count, cudaStream_t s, cudaEvent_t* ev, bool general,
-                           unsigned long long* checksums)
+                           unsigned long long* checksums, float* dx_plane)
     {
         if (ev) cudaEventRecord(ev[0], s);
         cudaLaunchAttribute attr[1];
@@ -1275,7 +1281,7 @@ struct Launch {
             cfg.gridDim = dim3(N / 2 / PAIRS, count);
             cfg.blockDim = dim3(3 * PAIRS * Cfg::T);
             cfg.dynamicSmemBytes = smem_rows_t;
-            e = cudaLaunchKernelEx(&cfg, k_rows_t<N, P, PAIRS, C, MINB>, h0, omega, tw, kx, gp, gh, time, first_tile);
+            e = cudaLaunchKernelEx(&cfg, k_rows_t<N, P, PAIRS, C, MINB>, h0, omega, tw, kx, gp, gh, time, first_tile, 0u);
         } else if (p->rows_mode == 0) {
             // measured on B200 (N=1024): PDL gains 21% / 7% at 1 / 4 tiles per launch (it hides ramp and tail) and
             // loses 1.5-3.5% at 8-16 tiles, so it is used while the row grid is below four waves
@@ -1311,8 +1317,8 @@ struct Launch {
         cfg.blockDim = dim3(CC::NTHREADS);
         cfg.dynamicSmemBytes = CC::SMEM;
         const float2 *cgp = p->d_gp, *cgh = p->d_gh;
-        e = general ? cudaLaunchKernelEx(&cfg, k_cols<N, P, C, true>, cgp, cgh, tw, out, first_tile, items, checksums)
-                    : cudaLaunchKernelEx(&cfg, k_cols<N, P, C, false>, cgp, cgh, tw, out, first_tile, items, checksums);
+        e = general ? cudaLaunchKernelEx(&cfg, k_cols<N, P, C, true>, cgp, cgh, tw, out, first_tile, items, checksums, dx_plane)
+                    : cudaLaunchKernelEx(&cfg, k_cols<N, P, C, false>, cgp, cgh, tw, out, first_tile, items, checksums, dx_plane);
         if (ev) cudaEventRecord(ev[2], s);
         return e;
     }
@@ -1460,16 +1466,16 @@ void fused_plan_destroy(FusedPlan* p)
 
 cudaError_t fused_enqueue(FusedPlan* p, const float2* h0, const float* omega, const OutDesc* out, float time,
                           uint32_t first_tile, uint32_t count, cudaStream_t s, uint32_t* launches, cudaEvent_t* ev,
-                          bool general, unsigned long long* checksums)
+                          bool general, unsigned long long* checksums, float* dx_plane)
 {
     cudaError_t e;
     switch (p->n) {
-        case 64: e = L64::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
-        case 128: e = L128::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
-        case 256: e = L256::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
-        case 512: e = L512::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
-        case 1024: e = L1024::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
-        case 2048: e = L2048::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums); break;
+        case 64: e = L64::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
+        case 128: e = L128::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
+        case 256: e = L256::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
+        case 512: e = L512::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
+        case 1024: e = L1024::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
+        case 2048: e = L2048::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
         default: return cudaErrorInvalidValue;
     }
     if (launches) *launches = 2;

@@ -67,6 +67,8 @@ struct ocean_ctx {
     ocean::FusedPlan* plan = nullptr;
     // normal map of the consumer step (lazy), float4[tile][y][x]
     float4* d_nrm = nullptr;
+    // OCEAN_FLAG_DX_PLANE: dense copy of channel .x per output buffer, float[buffer][tile][y][x], written by k_cols
+    float* d_dxp = nullptr;
     // ocean_debug_spectra scratch (lazy)
     float2* d_dbg = nullptr;
 
@@ -219,7 +221,7 @@ int ocean_create_ex(ocean_ctx** out, const ocean_config* cfg)
         return fail(nullptr, OCEAN_ERR_UNSUPPORTED, "literal pipeline supports N <= 2048");
     if (cfg->pipeline == OCEAN_PIPELINE_FUSED && !ocean::fused_supports(cfg->resolution))
         return fail(nullptr, OCEAN_ERR_UNSUPPORTED, "fused pipeline supports N in {64, 128, 256, 512, 1024, 2048}");
-    if (cfg->flags & ~(OCEAN_FLAG_KEEP_SPECTRA | OCEAN_FLAG_DOUBLE_BUFFER_OUTPUT))
+    if (cfg->flags & ~(OCEAN_FLAG_KEEP_SPECTRA | OCEAN_FLAG_DOUBLE_BUFFER_OUTPUT | OCEAN_FLAG_DX_PLANE))
         return fail(nullptr, OCEAN_ERR_INVALID_ARG, "unknown flag bits");
 
     int count = 0;
@@ -276,6 +278,9 @@ int ocean_create_ex(ocean_ctx** out, const ocean_config* cfg)
         if ((e = cudaMemcpy(c->d_out_tab[b], c->out_tab[b].data(), nt * sizeof(ocean::OutDesc), cudaMemcpyHostToDevice)) != cudaSuccess)
             return bail(e, "cudaMemcpy(out_tab)");
     }
+    if ((c->flags & OCEAN_FLAG_DX_PLANE) && c->pipeline == OCEAN_PIPELINE_FUSED && c->n >= 32) {
+        if ((e = cudaMalloc(&c->d_dxp, c->n_buffers * nt * np * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc(dx plane)");
+    }
     if (c->n_buffers == 2) {
         if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate(copy)");
         for (int b = 0; b < 2; ++b) {
@@ -323,6 +328,7 @@ void ocean_destroy(ocean_ctx* c)
     cudaFree(c->d_work);
     cudaFree(c->d_dbg);
     cudaFree(c->d_nrm);
+    cudaFree(c->d_dxp);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     (void)cudaGetLastError();
     delete c;
@@ -419,7 +425,8 @@ int enqueue_frame(ocean_ctx* c, float time, uint32_t first_tile, uint32_t count,
             const uint32_t cnt = t0 + batch <= first_tile + count ? batch : first_tile + count - t0;
             uint32_t nl = 0;
             OCEAN_CUDA(c, ocean::fused_enqueue(c->plan, c->d_h0, c->d_omega, c->d_out_tab[c->cur], time, t0, cnt, c->stream,
-                                               &nl, ev, c->any_pitched || sums != nullptr, sums ? sums + (t0 - first_tile) : nullptr));
+                                               &nl, ev, c->any_pitched || sums != nullptr, sums ? sums + (t0 - first_tile) : nullptr,
+                                               c->d_dxp ? c->d_dxp + size_t(c->cur) * c->n_tiles * pts(c) : nullptr));
             c->launches += nl;
         }
     }
@@ -605,7 +612,12 @@ int ocean_compute_normals(ocean_ctx* c, uint32_t first_tile, uint32_t count)
     bool own = true;                       // all tiles of the range in the context's own dense buffer: one launch
     for (uint32_t t = first_tile; t < first_tile + count; ++t)
         own &= tile_out(c, t) == c->d_out + (size_t(c->cur) * c->n_tiles + t) * pts(c);
-    if (own) {
+    if (c->d_dxp) {
+        // the column kernel left a dense copy of channel .x beside the map (external outputs included): 4 B/pt to read
+        OCEAN_CUDA(c, ocean::launch_normal_map_plane(c->d_dxp + (size_t(c->cur) * c->n_tiles + first_tile) * pts(c),
+                                                     c->d_nrm + first_tile * pts(c), c->n, count, c->stream));
+        c->launches += 1;
+    } else if (own) {
         OCEAN_CUDA(c, ocean::launch_normal_map(tile_out(c, first_tile), c->n, pts(c), c->d_nrm + first_tile * pts(c), c->n, count, c->stream));
         c->launches += 1;
     } else {

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (CorrectionLocals, OceanConfig, OceanError, PropagateLocals, SpectrumParams,  # noqa: F401
-                   PIPELINE_FUSED, PIPELINE_LITERAL, FLAG_DOUBLE_BUFFER_OUTPUT)
+                   PIPELINE_FUSED, PIPELINE_LITERAL, FLAG_DOUBLE_BUFFER_OUTPUT, FLAG_DX_PLANE)
 
 # src/render.rs:42-46
 WORKGROUP_SIZE = 16

@@ -96,6 +96,10 @@ typedef struct ocean_config {
  * shared image, src/lib.rs:86). ocean_output_device then returns the buffer of the latest update. Such a context
  * updates all of its tiles together and takes no external outputs. */
 #define OCEAN_FLAG_DOUBLE_BUFFER_OUTPUT 2u
+/* The column kernel also writes a dense float copy of channel .x (dx) of every map it produces (+4 B per grid point),
+ * which ocean_compute_normals then differentiates instead of gathering .x out of the RGBA texels: 20 instead of 32
+ * bytes per grid point for the normal map. For contexts that call ocean_compute_normals every frame. */
+#define OCEAN_FLAG_DX_PLANE 4u
 
 /* Parameters of ocean_generate_spectrum. Defaults when NULL: amplitude 3e-8 (max|h0| ~ 1 at L = 1000, the scale of the
  * reference's data/spectrum.bin, |h0| <= 1.198), wind 30 m/s along +x, g 9.81, depth 100 m */

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from gfx_ocean_b200 import FLAG_DOUBLE_BUFFER_OUTPUT, Ocean, OceanError, PIPELINE_LITERAL, _lib
+from gfx_ocean_b200 import FLAG_DOUBLE_BUFFER_OUTPUT, FLAG_DX_PLANE, Ocean, OceanError, PIPELINE_LITERAL, _lib
 from gfx_ocean_b200.spectrum import synthetic_tile
 from oracle.ocean_oracle import displace_grid_np, max_rel_err
 
@@ -224,3 +224,23 @@ def test_graph_replay_is_bit_identical_to_plain_launches():
         o.update(0.0)
         o.update_graph(0.9, 1, 2)                               # another tile range: another recorded graph
         np.testing.assert_array_equal(o.output_checksums()[1:], a[1:])
+
+
+@pytest.mark.parametrize("n,flags", [(1024, FLAG_DX_PLANE), (256, FLAG_DX_PLANE), (512, FLAG_DX_PLANE | FLAG_DOUBLE_BUFFER_OUTPUT)])
+def test_dx_plane_normals_are_bit_identical(n, flags):
+    """OCEAN_FLAG_DX_PLANE: the column kernel leaves a dense copy of channel .x; the normal map computed from it must
+    equal the one gathered from the RGBA texels bit for bit, and the displacement map itself is unchanged."""
+    tiles = 2
+    data = [synthetic_tile(n, g + 60) for g in range(tiles)]
+    res = []
+    for fl in (0, flags):
+        with Ocean(n, 1000.0, n_tiles=tiles, flags=fl) as o:
+            for i, (h0, w) in enumerate(data):
+                o.set_spectrum(i, h0, w)
+            for t in (0.5, 1.5, 2.5):                      # three frames: both buffers of a double-buffered context
+                o.update(t)
+                o.compute_normals()
+            res.append(([o.read_back(i) for i in range(tiles)], [o.read_back_normals(i) for i in range(tiles)]))
+    for i in range(tiles):
+        np.testing.assert_array_equal(res[0][0][i], res[1][0][i])
+        np.testing.assert_array_equal(res[0][1][i], res[1][1][i])
