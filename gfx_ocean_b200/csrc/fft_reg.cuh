@@ -58,9 +58,36 @@ __host__ __device__ constexpr double cos2pi(long k, long n)
 
 __host__ __device__ constexpr double sin2pi(long k, long n) { return cos2pi(4 * k - n, 4 * n); }  // sin t = cos(t - pi/2)
 
+// OCEAN_FFT_PACKED (device code, sm_100+): 1 = the twiddle-free butterflies (w = 1: 31 of the 80 butterflies of a
+// 32-point transform) use the packed add.rn.f32x2 / fma.rn.f32x2 on the (re, im) register pair -- two instructions
+// instead of four; 2 = the general butterflies use fma.rn.f32x2 as well (three packed FMAs + the swapped operand).
+// 0 = scalar (default). Measured on B200 (1024^2 x 8 tiles): 80.2 k / 79.2 k / 79.4 k frames/s for 0 / 1 / 2 -- the
+// static instruction count of k_rows_t drops 2880 -> 2800 -> 2640 but the kernels are latency bound, not issue bound,
+// and the scalar form keeps its twiddles as FFMA immediates.
+#ifndef OCEAN_FFT_PACKED
+#define OCEAN_FFT_PACKED 0
+#endif
+
 template <int R, int K>
 __host__ __device__ __forceinline__ void dit_butterfly(const float2 e, const float2 o, float2& lo, float2& hi)
 {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000 && OCEAN_FFT_PACKED >= 1
+    if constexpr (K == 0) {
+        lo = __fadd2_rn(e, o);
+        hi = __ffma2_rn(o, make_float2(-1.0f, -1.0f), e);      // e - o, exact like a subtraction
+        return;
+    }
+#if OCEAN_FFT_PACKED >= 2
+    if constexpr (4 * K != R) {
+        constexpr float wr = float(cos2pi(K, R));
+        constexpr float wi = float(sin2pi(K, R));
+        const float2 t = __ffma2_rn(make_float2(wr, wr), o, e);                        // e + wr o
+        lo = __ffma2_rn(make_float2(-wi, wi), make_float2(o.y, o.x), t);               // + (-wi o.y, wi o.x)
+        hi = __ffma2_rn(make_float2(2.0f, 2.0f), e, make_float2(-lo.x, -lo.y));        // 2e - lo
+        return;
+    }
+#endif
+#endif
     if constexpr (K == 0) {
         lo = make_float2(e.x + o.x, e.y + o.y);
         hi = make_float2(e.x - o.x, e.y - o.y);

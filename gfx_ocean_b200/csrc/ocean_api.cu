@@ -59,6 +59,7 @@ struct ocean_ctx {
         float time;
     };
     std::vector<FrameGraph*> graphs;
+    bool capturing = false;
     // literal pipeline: dx_spec | dy_spec | dz_spec of the tile in flight (src/render.rs:608-646)
     float2* d_spec = nullptr;
     // fused pipeline: row-pass output, consumed by the column pass
@@ -420,7 +421,7 @@ int enqueue_frame(ocean_ctx* c, float time, uint32_t first_tile, uint32_t count,
         // tiles per kernel pair: the whole range by default; OCEAN_B200_BATCH=k splits it so that a batch's row-pass
         // output is still in L2 when its column pass reads it (experiment knob)
         static const uint32_t batch_env = [] { const char* v = std::getenv("OCEAN_B200_BATCH"); return v ? uint32_t(std::atoi(v)) : 0u; }();
-        const uint32_t batch = (batch_env && !ev) ? batch_env : count;
+        const uint32_t batch = (batch_env && !ev && !c->capturing) ? batch_env : count;   // a recorded frame is one kernel pair
         for (uint32_t t0 = first_tile; t0 < first_tile + count; t0 += batch) {
             const uint32_t cnt = t0 + batch <= first_tile + count ? batch : first_tile + count - t0;
             uint32_t nl = 0;
@@ -492,7 +493,9 @@ int ocean_update_graph(ocean_ctx* c, float time, uint32_t first_tile, uint32_t c
         if (!g) return fail(c, OCEAN_ERR_CUDA, "out of host memory");
         const uint64_t launches_before = c->launches;
         cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+        c->capturing = true;
         int rc = e == cudaSuccess ? enqueue_frame(c, time, first_tile, count, nullptr, nullptr) : cuda_fail(c, e, "cudaStreamBeginCapture");
+        c->capturing = false;
         if (e == cudaSuccess) {
             e = cudaStreamEndCapture(c->stream, &g->graph);
             if (rc == OCEAN_OK && e != cudaSuccess) rc = cuda_fail(c, e, "cudaStreamEndCapture");

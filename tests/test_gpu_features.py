@@ -244,3 +244,25 @@ def test_dx_plane_normals_are_bit_identical(n, flags):
     for i in range(tiles):
         np.testing.assert_array_equal(res[0][0][i], res[1][0][i])
         np.testing.assert_array_equal(res[0][1][i], res[1][1][i])
+
+
+def test_split_launches_are_bit_identical():
+    """OCEAN_B200_BATCH splits an update into several kernel pairs that reuse one intermediate region; same bits."""
+    n, tiles = 512, 5
+    data = [synthetic_tile(n, g + 70) for g in range(tiles)]
+    sums = []
+    for kv in (dict(OCEAN_B200_BATCH=None), dict(OCEAN_B200_BATCH="2")):
+        import subprocess, sys, json            # the knob is read once per process: run each setting in its own process
+        code = ("import sys, json; sys.path.insert(0, %r); import numpy as np; from gfx_ocean_b200 import Ocean; "
+                "from gfx_ocean_b200.spectrum import synthetic_tile; o = Ocean(%d, 1000.0, n_tiles=%d); "
+                "[o.set_spectrum(i, *synthetic_tile(%d, i + 70)) for i in range(%d)]; "
+                "s = o.update_sequence_checksums(0.0, 0.25, 6); print(json.dumps(s.tolist()))" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), n, tiles, n, tiles))
+        env_ = dict(os.environ)
+        env_.pop("OCEAN_B200_BATCH", None)
+        if kv["OCEAN_B200_BATCH"]:
+            env_["OCEAN_B200_BATCH"] = kv["OCEAN_B200_BATCH"]
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env_, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        sums.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert sums[0] == sums[1]
+    del data
