@@ -196,8 +196,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{n}x{n} x3 fields (height, dx, dz), {tiles} independent tiles per GPU per step; "
                                "frame = one tile's propagate -> 2-D iFFT -> correction -> RGBA32F map",
-                   "resolution": n, "tiles_per_gpu": tiles,
-                   "implementation": "CPU literal fp32 restatement of the reference shaders (oracle/ocean_oracle.c, OpenMP)"},
+                   "resolution": n, "tiles_per_gpu": tiles, "total_tiles": tiles * max(args.gpus, 1),
+                   "implementation": "CPU literal fp32 restatement of the reference shaders (oracle/ocean_oracle.c, OpenMP); "
+                                     "rank 0 times one GPU's share of the tiles"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{steps} steps x {tiles} tile-frames at {n}x{n} in {el:.1f} s"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

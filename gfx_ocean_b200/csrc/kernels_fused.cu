@@ -385,6 +385,9 @@ __device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1
 #ifndef OCEAN_ROWS_T_PREFETCH
 #define OCEAN_ROWS_T_PREFETCH 0
 #endif
+#ifndef OCEAN_ROWS_T_UNROLL
+#define OCEAN_ROWS_T_UNROLL 2           // point pairs of phase A in flight per thread
+#endif
 template <int N>
 struct RowSlot {
     static constexpr uint32_t REV_OFF = 8u * (N + 2), OM_OFF = 16u * (N + 2), BYTES = OM_OFF + 4u * N;
@@ -479,7 +482,8 @@ k_rows_t(const float2* __restrict__ h0_all, const float* __restrict__ omega_all,
         float4* R4 = reinterpret_cast<float4*>(sl.rev());
         const float2* W2 = reinterpret_cast<const float2*>(sl.om());
         const float2* __restrict__ pk = reinterpret_cast<const float2*>(kx_g);
-#pragma unroll 2
+        constexpr int kUnrollA = OCEAN_ROWS_T_UNROLL;
+#pragma unroll kUnrollA
         for (int i = tid; i < N / 2; i += NT) {
             const float2 w = W2[i];
             const float4 a = F4[i], b = R4[N / 2 - 1 - i];     // b.zw is the partner of x = 2 i, b.xy the partner of x + 1

@@ -736,7 +736,10 @@ int ocean_profile_update(ocean_ctx* c, float time, float* stage_ms, uint32_t cap
         if (ce != cudaSuccess) { rc = cuda_fail(c, ce, "cudaEventCreate"); break; }
     }
     if (rc == OCEAN_OK && c->pipeline == OCEAN_PIPELINE_FUSED) {
-        rc = enqueue_frame(c, time, 0, c->n_tiles, nullptr, ev.data());
+        // an unmeasured frame first: the measured kernels are already queued behind it when it finishes, so the
+        // intervals between the events are kernel durations, not host launch latency after an idle stream
+        rc = enqueue_frame(c, time, 0, c->n_tiles, nullptr, nullptr);
+        if (rc == OCEAN_OK) rc = enqueue_frame(c, time, 0, c->n_tiles, nullptr, ev.data());
     } else if (rc == OCEAN_OK) {
         // LITERAL: tile 0 only, stage by stage in the reference's dispatch order (src/render.rs:1122-1287)
         c->plocals = {time, int32_t(c->n), c->domain_size};

@@ -190,9 +190,11 @@ OCEAN_API int  ocean_displace_grid(ocean_ctx* ctx, uint32_t tile, uint32_t grid,
 OCEAN_API int  ocean_displace_grid_device(ocean_ctx* ctx, uint32_t tile, uint32_t grid, float offset_x, float offset_z, float* d_pos_world);
 
 /* ---- measurement */
-/* One update with CUDA events recorded on the context's stream around every kernel of the frame;
- * waits, then writes each kernel's duration in ms (FUSED: [k_rows, k_cols]; LITERAL: the 8
- * dispatches in reference order). *n_stages receives the count; capacity is stage_ms's length. */
+/* One update with CUDA events recorded on the context's stream around every kernel of the frame (FUSED: after an
+ * unmeasured frame of the same kind, so that the intervals are kernel durations and not launch latency; the events
+ * serialise the two kernels, which otherwise overlap under programmatic dependent launch). Waits, then writes each
+ * kernel's duration in ms (FUSED: [row kernel, k_cols] over all tiles; LITERAL: the 8 dispatches of tile 0 in
+ * reference order). *n_stages receives the count; capacity is stage_ms's length. */
 OCEAN_API int  ocean_profile_update(ocean_ctx* ctx, float time, float* stage_ms, uint32_t capacity, uint32_t* n_stages);
 
 /* ---- introspection */
