@@ -97,3 +97,20 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "ocean_oracle" not in txt and "oracle/" not in txt and "import oracle" not in txt, f
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 (no C++-isms), and every declared entry point links."""
+    src = tmp_path / "use.c"
+    calls = "\n".join(f"    p[{i}] = (void*){s};" for i, s in enumerate(header_symbols()))
+    src.write_text('#include "ocean_b200.h"\n#include <stdio.h>\nint main(void) {\n    void* p[%d];\n%s\n'
+                   '    ocean_spectrum_params sp = {3e-8f, 30.0f, 9.81f, 100.0f}; ocean_config cfg; (void)sp; (void)cfg;\n'
+                   '    printf("%%u %%p\\n", ocean_abi_version(), p[0]);\n    return 0;\n}\n' % (len(header_symbols()), calls))
+    exe = tmp_path / "use"
+    build()
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe), "-L", os.path.dirname(_lib.LIB_PATH), "-l:libocean_b200.so",
+                        "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split()[0] == str(_lib.ABI_VERSION)
