@@ -11,6 +11,9 @@ context = one frame of every tile; one *frame* = one tile's propagate -> 2-D inv
 -> RGBA32F displacement map. With 8 tiles a step touches 96 MB of inputs + 128 MB of outputs
 (+ intermediates), more than the 126 MB L2, so every step's inputs come from HBM ("inputs larger than L2").
 
+Headline call: ocean_update_overlapped (frames alternate between two internal lanes; same maps as ocean_update bit for
+bit); `plain_updates` reports ocean_update beside it.
+
 Timing: W warm-up steps, then R >= 5 repetitions of EXACTLY K steps, each bracketed by barrier +
 synchronize and timed with CUDA events on the launching stream (max over ranks); R grows until the
 repetitions add up to >= --min-time seconds, so a small K still gives a stable number. `value` is the
@@ -278,10 +281,26 @@ def main():
             reps.append(timed(fn, steps))
         return reps
 
-    # ---- device-resident throughput: R repetitions of K steps, inputs already in HBM
+    # ---- device-resident throughput: R repetitions of K steps, inputs already in HBM.
+    #      Headline: ocean_update_overlapped -- consecutive frames alternate between two lanes (stream + own row-pass
+    #      intermediate), so the row kernel of step n+1 runs beside the column kernel of step n; bit-identical maps
+    #      (tests/test_gpu_features.py). The closing event is recorded behind ocean_join, i.e. after both lanes drained.
+    #      plain_updates: the same steps through ocean_update (one stream, kernels chained by programmatic dependent launch).
+    lanes_ok = args.pipeline == "fused"
+
+    def headline_step(i):
+        if lanes_ok:
+            ocean.update_overlapped(args.dt * (W + i))
+            if i == K - 1:
+                ocean.join()
+        else:
+            ocean.update(args.dt * (W + i))
+
     with torch.cuda.stream(stream):
         for i in range(W):
             ocean.update(args.dt * i)
+            if lanes_ok:
+                ocean.update_overlapped(args.dt * i)
         barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
@@ -289,11 +308,16 @@ def main():
             for i in range(max(1, int(0.4 / 1.2e-4))):      # keep the GPU loaded while nvidia-smi spins up
                 ocean.update(args.dt * i)
         l0 = ocean.launch_count
-        reps = repeated(lambda i: ocean.update(args.dt * (W + i)), K, args.reps, args.min_time)
+        reps = repeated(headline_step, K, args.reps, args.min_time)
         launches = (ocean.launch_count - l0) // len(reps)
         clocks = sampler.stop() if rank == 0 else None
+        reps_plain = repeated(lambda i: ocean.update(args.dt * (W + i)), K, args.reps, args.min_time) if lanes_ok else reps
     ms = statistics.median(reps)
     fps = total_tiles * K / (ms * 1e-3)
+    ms_plain = statistics.median(reps_plain)
+    plain = {"value": total_tiles * K / (ms_plain * 1e-3), "unit": UNIT, "ms_per_step": ms_plain / K, "repetitions": len(reps_plain),
+             "alg_GBps": ALG_BYTES_PER_POINT * n * n * tiles / (ms_plain / K * 1e-3) / 1e9,
+             "note": "the same steps through ocean_update: one stream, k_rows_t / k_cols chained by programmatic dependent launch"}
 
     # ---- tile determinism: every tile's checksum at a fixed time, gathered; rank 0 recomputes ALL tiles on its own
     #      GPU (tile g = generate_spectrum(SEED, stream_id=g) anywhere) and compares bit for bit
@@ -337,14 +361,25 @@ def main():
                 ocean.update_graph(args.dt * i, i % tiles, 1)
             r_plain = repeated(lambda i: ocean.update_tiles(args.dt * i, i % tiles, 1), ks, 5, 0.2)
             r_graph = repeated(lambda i: ocean.update_graph(args.dt * i, i % tiles, 1), ks, 5, 0.2)
+            for i in range(W):
+                ocean.update_overlapped(args.dt * i, i % tiles, 1)
+            ocean.sync()
+
+            def lanes(i):
+                ocean.update_overlapped(args.dt * i, i % tiles, 1)
+                if i == ks - 1:
+                    ocean.join()                 # the closing event is recorded behind both lanes
+            r_lanes = repeated(lanes, ks, 5, 0.2)
 
         def lat(r):
             m = statistics.median(r)
             return {"value": world * ks / (m * 1e-3), "unit": UNIT, "us_per_frame": 1e3 * m / ks,
                     "alg_GBps": ALG_BYTES_PER_POINT * n * n / (m / ks * 1e-3) / 1e9}
-        single = {"plain": lat(r_plain), "graph": lat(r_graph), "steps": ks, "repetitions": len(r_plain),
+        single = {"plain": lat(r_plain), "graph": lat(r_graph), "overlapped": lat(r_lanes), "steps": ks, "repetitions": len(r_plain),
                   "note": "one tile per ocean_update (2 launches), rotating over the tiles so inputs are L2-cold; "
-                          "plain = cudaLaunchKernelEx per kernel, graph = ocean_update_graph replay"}
+                          "plain = cudaLaunchKernelEx per kernel, graph = ocean_update_graph replay, overlapped = "
+                          "ocean_update_overlapped (consecutive frames, which are different tiles, alternate between two "
+                          "lanes: the row kernel of frame n+1 runs beside the column kernel of frame n)"}
         single.update(single["plain"])      # keep round 1's flat keys
 
     # ---- per-kernel durations (CUDA events between the two launches, same stream)
@@ -480,6 +515,7 @@ def main():
             "config": {"workload": f"{n}x{n} x3 fields (height, dx, dz), {tiles} independent tiles per GPU per step; "
                                    "frame = one tile's propagate -> 2-D iFFT -> correction -> RGBA32F map",
                        "resolution": n, "tiles_per_gpu": tiles, "total_tiles": total_tiles, "pipeline": args.pipeline,
+                       "update_call": "ocean_update_overlapped (two lanes)" if lanes_ok else "ocean_update",
                        "inputs": f"ocean_generate_spectrum(seed={SEED}, stream_id=global tile) on the device",
                        "l2": "inputs larger than L2 (per-step working set %.0f MB > 126 MB)" % (
                            (12 + 12 + 16) * n * n * tiles / 1e6),
@@ -499,6 +535,7 @@ def main():
             "step_alg_GBps": alg_step / (ms / K * 1e-3) / 1e9,
             "step_frac_of_measured_peak": alg_step / (ms / K * 1e-3) / 1e9 / peak,
             "step_real_bytes_frac": REAL_BYTES_PER_POINT * n * n * tiles / (ms / K * 1e-3) / 1e9 / peak,
+            "plain_updates": plain,
             "tile_determinism": determinism,
             "single_tile_per_update": single,
             "with_normals": with_normals,

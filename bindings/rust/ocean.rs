@@ -77,6 +77,8 @@ extern "C" {
     pub fn ocean_update(ctx: *mut ocean_ctx, time: f32) -> c_int;
     pub fn ocean_update_tiles(ctx: *mut ocean_ctx, time: f32, first_tile: u32, count: u32) -> c_int;
     pub fn ocean_update_graph(ctx: *mut ocean_ctx, time: f32, first_tile: u32, count: u32) -> c_int;
+    pub fn ocean_update_overlapped(ctx: *mut ocean_ctx, time: f32, first_tile: u32, count: u32) -> c_int;
+    pub fn ocean_join(ctx: *mut ocean_ctx) -> c_int;
     pub fn ocean_update_sequence(ctx: *mut ocean_ctx, t0: f32, dt: f32, n_frames: u32) -> c_int;
     pub fn ocean_update_sequence_checksums(ctx: *mut ocean_ctx, t0: f32, dt: f32, n_frames: u32, h_sums: *mut u64) -> c_int;
     pub fn ocean_output_checksums(ctx: *mut ocean_ctx, h_sums: *mut u64) -> c_int;

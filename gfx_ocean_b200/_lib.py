@@ -57,6 +57,8 @@ SIGNATURES = {
     "ocean_update_tiles": (C.c_int, [_P, _F, _U32, _U32]),
     "ocean_update_sequence": (C.c_int, [_P, _F, _F, _U32]),
     "ocean_update_graph": (C.c_int, [_P, _F, _U32, _U32]),
+    "ocean_update_overlapped": (C.c_int, [_P, _F, _U32, _U32]),
+    "ocean_join": (C.c_int, [_P]),
     "ocean_output_device": (C.c_int, [_P, _U32, C.POINTER(_P)]),
     "ocean_download": (C.c_int, [_P, _U32, _P]),
     "ocean_download_async": (C.c_int, [_P, _U32, _P]),

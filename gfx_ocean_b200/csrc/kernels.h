@@ -47,11 +47,13 @@ struct OutDesc {
 // Enqueue one frame for tiles [first_tile, first_tile + count); *launches = kernels launched.
 // out_tab: device array of OutDesc indexed by tile; `general` selects the k_cols build that honours row pitches
 // != N and (checksums != nullptr) adds every tile's output checksum into checksums[tile - first_tile];
-// dx_plane (optional): dense float[tile][y][x] copy of channel .x for the normal-map kernel.
+// dx_plane (optional): dense float[tile][y][x] copy of channel .x for the normal-map kernel;
+// lane 0 / 1: which of the plan's two intermediate sets the frame uses (frames in flight on different streams must differ);
+// cols_after (optional): an event the column kernel (which writes the maps) is ordered behind.
 // If `ev` is non-null it holds 3 events recorded before, between and after the two kernels.
 cudaError_t fused_enqueue(FusedPlan* p, const float2* h0, const float* omega, const OutDesc* out_tab, float time,
                           uint32_t first_tile, uint32_t count, cudaStream_t s, uint32_t* launches,
                           cudaEvent_t* ev = nullptr, bool general = false, unsigned long long* checksums = nullptr,
-                          float* dx_plane = nullptr);
+                          float* dx_plane = nullptr, int lane = 0, cudaEvent_t cols_after = nullptr);
 
 }  // namespace ocean

@@ -1222,6 +1222,8 @@ struct FusedPlan {
     float* d_kx = nullptr;       // [N] wave numbers, propagate.comp:45-46,50-53
     float2* d_gp = nullptr;      // [tiles] strip-major packed (dx, dz) row-pass output
     float2* d_gh = nullptr;      // [tiles] strip-major height row-pass output (N/2 rows)
+    float2* d_gp2 = nullptr;     // a second set (allocated on demand) for frames enqueued on the second lane, so that two
+    float2* d_gh2 = nullptr;     // frames in flight on different streams never share an intermediate (ocean_update_overlapped)
     size_t gp_per_tile = 0, gh_per_tile = 0;   // float2 per tile
 };
 
@@ -1262,7 +1264,7 @@ struct Launch {
 
     static cudaError_t run(FusedPlan* p, const float2* h0, const float* omega, const OutDesc* out, float time,
                            uint32_t first_tile, uint32_t count, cudaStream_t s, cudaEvent_t* ev, bool general,
-                           unsigned long long* checksums, float* dx_plane)
+                           unsigned long long* checksums, float* dx_plane, int lane, cudaEvent_t cols_after)
     {
         if (ev) cudaEventRecord(ev[0], s);
         cudaLaunchAttribute attr[1];
@@ -1273,7 +1275,7 @@ struct Launch {
         cfg.numAttrs = 1;
         const float2* tw = p->d_tw;
         const float* kx = p->d_kx;
-        float2 *gp = p->d_gp, *gh = p->d_gh;
+        float2 *gp = lane ? p->d_gp2 : p->d_gp, *gh = lane ? p->d_gh2 : p->d_gh;
         cudaError_t e;
         static const bool debug_env = std::getenv("OCEAN_B200_DEBUG") != nullptr;
         const bool skip_rows = debug_env && std::getenv("OCEAN_B200_DEBUG_SKIP_ROWS") != nullptr;   // re-run k_cols on the same intermediate
@@ -1315,12 +1317,19 @@ struct Launch {
         }
         if (e != cudaSuccess) return e;
         if (ev) cudaEventRecord(ev[1], s);
+        // the column kernel writes the maps: order it behind the frame that wrote the same maps on the other lane. It is
+        // then launched as an ordinary stream-ordered kernel: a programmatic launch is tied to the preceding KERNEL and
+        // would start past the event wait that sits between the two.
+        if (cols_after) {
+            if ((e = cudaStreamWaitEvent(s, cols_after, 0)) != cudaSuccess) return e;
+            attr[0].val.programmaticStreamSerializationAllowed = 0;
+        }
         const uint32_t items = count * (N / C);
         const uint32_t slots = uint32_t(p->num_sms * p->cols_blocks_per_sm);
         cfg.gridDim = dim3(items < slots ? items : slots);
         cfg.blockDim = dim3(CC::NTHREADS);
         cfg.dynamicSmemBytes = CC::SMEM;
-        const float2 *cgp = p->d_gp, *cgh = p->d_gh;
+        const float2 *cgp = gp, *cgh = gh;
         e = general ? cudaLaunchKernelEx(&cfg, k_cols<N, P, C, true>, cgp, cgh, tw, out, first_tile, items, checksums, dx_plane)
                     : cudaLaunchKernelEx(&cfg, k_cols<N, P, C, false>, cgp, cgh, tw, out, first_tile, items, checksums, dx_plane);
         if (ev) cudaEventRecord(ev[2], s);
@@ -1465,21 +1474,32 @@ void fused_plan_destroy(FusedPlan* p)
     cudaFree(p->d_kx);
     cudaFree(p->d_gp);
     cudaFree(p->d_gh);
+    cudaFree(p->d_gp2);
+    cudaFree(p->d_gh2);
     delete p;
 }
 
 cudaError_t fused_enqueue(FusedPlan* p, const float2* h0, const float* omega, const OutDesc* out, float time,
                           uint32_t first_tile, uint32_t count, cudaStream_t s, uint32_t* launches, cudaEvent_t* ev,
-                          bool general, unsigned long long* checksums, float* dx_plane)
+                          bool general, unsigned long long* checksums, float* dx_plane, int lane, cudaEvent_t cols_after)
 {
+    if (lane && !p->d_gp2) {
+        // second intermediate set, same size as the first; pad rows are zeroed once like the first set's
+        const size_t gpb = size_t(p->n_tiles) * p->gp_per_tile * sizeof(float2), ghb = size_t(p->n_tiles) * p->gh_per_tile * sizeof(float2);
+        cudaError_t a = cudaMalloc(&p->d_gp2, gpb);
+        if (a == cudaSuccess) a = cudaMalloc(&p->d_gh2, ghb);
+        if (a == cudaSuccess) a = cudaMemset(p->d_gp2, 0, gpb);
+        if (a == cudaSuccess) a = cudaMemset(p->d_gh2, 0, ghb);
+        if (a != cudaSuccess) return a;
+    }
     cudaError_t e;
     switch (p->n) {
-        case 64: e = L64::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
-        case 128: e = L128::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
-        case 256: e = L256::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
-        case 512: e = L512::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
-        case 1024: e = L1024::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
-        case 2048: e = L2048::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane); break;
+        case 64: e = L64::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane, lane, cols_after); break;
+        case 128: e = L128::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane, lane, cols_after); break;
+        case 256: e = L256::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane, lane, cols_after); break;
+        case 512: e = L512::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane, lane, cols_after); break;
+        case 1024: e = L1024::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane, lane, cols_after); break;
+        case 2048: e = L2048::run(p, h0, omega, out, time, first_tile, count, s, ev, general, checksums, dx_plane, lane, cols_after); break;
         default: return cudaErrorInvalidValue;
     }
     if (launches) *launches = 2;

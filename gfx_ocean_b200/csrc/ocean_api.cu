@@ -60,6 +60,16 @@ struct ocean_ctx {
     };
     std::vector<FrameGraph*> graphs;
     bool capturing = false;
+    // ocean_update_overlapped: two lanes (stream + own intermediate set), frames alternate between them
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;       // the lane's latest frame is complete
+        uint32_t first = 0, count = 0;    // its tile range
+        bool busy = false;
+    } lanes[2];
+    cudaEvent_t ev_main = nullptr;        // work enqueued on the main stream that the lanes must see (inputs, output routing)
+    bool main_dirty = true;               // the main stream saw activity since the lanes last synchronised with it
+    uint32_t next_lane = 0;
     // literal pipeline: dx_spec | dy_spec | dz_spec of the tile in flight (src/render.rs:608-646)
     float2* d_spec = nullptr;
     // fused pipeline: row-pass output, consumed by the column pass
@@ -120,9 +130,25 @@ struct DeviceGuard {
         if (prev >= 0 && prev != dev) cudaSetDevice(prev);
     }
 };
+int join_lanes(ocean_ctx* c);
+// Entry points that enqueue on (or synchronise with) the context's main stream: run on its device and first order the
+// main stream behind any frame still in flight on the lanes of ocean_update_overlapped.
 #define OCEAN_ON_DEVICE(ctx)                                             \
     DeviceGuard guard_((ctx)->device);                                   \
-    if (guard_.err != cudaSuccess) return cuda_fail((ctx), guard_.err, "cudaSetDevice")
+    if (guard_.err != cudaSuccess) return cuda_fail((ctx), guard_.err, "cudaSetDevice"); \
+    (ctx)->main_dirty = true;                                            \
+    if (int jrc_ = join_lanes(ctx)) return jrc_
+
+// Everything but ocean_update_overlapped runs on the main stream: make it wait for frames still in flight on the lanes.
+int join_lanes(ocean_ctx* c)
+{
+    for (auto& l : c->lanes)
+        if (l.busy) {
+            OCEAN_CUDA(c, cudaStreamWaitEvent(c->stream, l.done, 0));
+            l.busy = false;
+        }
+    return OCEAN_OK;
+}
 
 float4* tile_out(const ocean_ctx* c, uint32_t tile) { return c->out_tab[c->cur][tile].base; }
 size_t tile_pitch(const ocean_ctx* c, uint32_t tile) { return c->out_tab[c->cur][tile].pitch; }
@@ -314,6 +340,14 @@ void ocean_destroy(ocean_ctx* c)
         if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]);
         cudaFree(c->d_out_tab[b]);
     }
+    for (auto& l : c->lanes) {
+        if (l.stream) {
+            cudaStreamSynchronize(l.stream);
+            cudaStreamDestroy(l.stream);
+        }
+        if (l.done) cudaEventDestroy(l.done);
+    }
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
     for (auto* g : c->graphs) {
         cudaGraphExecDestroy(g->exec);
         cudaGraphDestroy(g->graph);
@@ -396,8 +430,11 @@ int ocean_load_bincode(ocean_ctx* c, uint32_t tile, const char* omega_path, cons
 namespace {
 
 // One frame for tiles [first_tile, first_tile + count); sums (optional, device): per-tile checksum accumulators.
-int enqueue_frame(ocean_ctx* c, float time, uint32_t first_tile, uint32_t count, unsigned long long* sums, cudaEvent_t* ev)
+// lane_stream / lane: enqueue on that stream with the plan's second intermediate set (ocean_update_overlapped).
+int enqueue_frame(ocean_ctx* c, float time, uint32_t first_tile, uint32_t count, unsigned long long* sums, cudaEvent_t* ev,
+                  cudaStream_t lane_stream = nullptr, int lane = 0, cudaEvent_t cols_after = nullptr)
 {
+    cudaStream_t st = lane_stream ? lane_stream : c->stream;
     c->plocals = {time, int32_t(c->n), c->domain_size};      // src/render.rs:1101-1120
     c->clocals = {c->n};
     if (c->n_buffers == 2) {
@@ -425,9 +462,9 @@ int enqueue_frame(ocean_ctx* c, float time, uint32_t first_tile, uint32_t count,
         for (uint32_t t0 = first_tile; t0 < first_tile + count; t0 += batch) {
             const uint32_t cnt = t0 + batch <= first_tile + count ? batch : first_tile + count - t0;
             uint32_t nl = 0;
-            OCEAN_CUDA(c, ocean::fused_enqueue(c->plan, c->d_h0, c->d_omega, c->d_out_tab[c->cur], time, t0, cnt, c->stream,
+            OCEAN_CUDA(c, ocean::fused_enqueue(c->plan, c->d_h0, c->d_omega, c->d_out_tab[c->cur], time, t0, cnt, st,
                                                &nl, ev, c->any_pitched || sums != nullptr, sums ? sums + (t0 - first_tile) : nullptr,
-                                               c->d_dxp ? c->d_dxp + size_t(c->cur) * c->n_tiles * pts(c) : nullptr));
+                                               c->d_dxp ? c->d_dxp + size_t(c->cur) * c->n_tiles * pts(c) : nullptr, lane, cols_after));
             c->launches += nl;
         }
     }
@@ -524,6 +561,50 @@ int ocean_update_graph(ocean_ctx* c, float time, uint32_t first_tile, uint32_t c
     c->plocals = {time, int32_t(c->n), c->domain_size};
     c->launches += 2;
     c->updated = true;
+    return OCEAN_OK;
+}
+
+int ocean_update_overlapped(ocean_ctx* c, float time, uint32_t first_tile, uint32_t count)
+{
+    if (!c) return OCEAN_ERR_INVALID_ARG;
+    if (int rc = check_range(c, first_tile, count, true)) return rc;
+    if (c->pipeline != OCEAN_PIPELINE_FUSED || c->n_buffers != 1)
+        return fail(c, OCEAN_ERR_UNSUPPORTED, "overlapped updates are available for the fused pipeline on a single-buffered context");
+    DeviceGuard guard(c->device);
+    if (guard.err != cudaSuccess) return cuda_fail(c, guard.err, "cudaSetDevice");
+    if (!c->ev_main) {
+        for (auto& l : c->lanes) {
+            OCEAN_CUDA(c, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+            OCEAN_CUDA(c, cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        }
+        OCEAN_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    }
+    const uint32_t li = c->next_lane;
+    auto& L = c->lanes[li];
+    auto& O = c->lanes[li ^ 1u];
+    if (c->main_dirty) {
+        // uploads, output routing and plain updates enqueued on the main stream come first, on both lanes
+        OCEAN_CUDA(c, cudaEventRecord(c->ev_main, c->stream));
+        OCEAN_CUDA(c, cudaStreamWaitEvent(c->lanes[0].stream, c->ev_main, 0));
+        OCEAN_CUDA(c, cudaStreamWaitEvent(c->lanes[1].stream, c->ev_main, 0));
+        c->main_dirty = false;
+    }
+    // The frame in flight on the other lane uses the other intermediate set, so this frame's row kernel never has to
+    // wait for it; only when both frames write the same maps is this frame's COLUMN kernel ordered behind that frame.
+    const bool same_maps = O.busy && first_tile < O.first + O.count && O.first < first_tile + count;
+    if (int rc = enqueue_frame(c, time, first_tile, count, nullptr, nullptr, L.stream, int(li), same_maps ? O.done : nullptr)) return rc;
+    OCEAN_CUDA(c, cudaEventRecord(L.done, L.stream));
+    L.busy = true;
+    L.first = first_tile;
+    L.count = count;
+    c->next_lane = li ^ 1u;
+    return OCEAN_OK;
+}
+
+int ocean_join(ocean_ctx* c)
+{
+    if (!c) return OCEAN_ERR_INVALID_ARG;
+    OCEAN_ON_DEVICE(c);
     return OCEAN_OK;
 }
 

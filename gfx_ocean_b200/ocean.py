@@ -99,6 +99,14 @@ class Ocean:
         """update_tiles through a recorded CUDA graph (replayed with `time` patched)."""
         self._check(self._lib.ocean_update_graph(self._ctx, time, first_tile, self.n_tiles - first_tile if count is None else count))
 
+    def update_overlapped(self, time: float, first_tile: int = 0, count: int | None = None) -> None:
+        """update_tiles on alternating internal lanes: frames of different tiles overlap on the device."""
+        self._check(self._lib.ocean_update_overlapped(self._ctx, time, first_tile, self.n_tiles - first_tile if count is None else count))
+
+    def join(self) -> None:
+        """Order the context's stream behind the frames in flight on the lanes (no host blocking)."""
+        self._check(self._lib.ocean_join(self._ctx))
+
     def update_sequence(self, t0: float, dt: float, n_frames: int) -> None:
         self._check(self._lib.ocean_update_sequence(self._ctx, t0, dt, n_frames))
 

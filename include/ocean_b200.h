@@ -143,6 +143,16 @@ OCEAN_API int  ocean_update_tiles(ocean_ctx* ctx, float time, uint32_t first_til
 /* ocean_update_tiles through a CUDA graph: the frame's launches (with their programmatic dependency) are recorded
  * once per tile range and replayed with only `time` patched (FUSED pipeline, single-buffered contexts). */
 OCEAN_API int  ocean_update_graph(ocean_ctx* ctx, float time, uint32_t first_tile, uint32_t count);
+/* ocean_update_tiles with consecutive frames in flight together: calls alternate between two internal lanes (stream +
+ * own row-pass intermediate), so the row kernel of one frame runs beside the column kernel of the previous one instead
+ * of waiting for it. When both frames write the same maps (same tiles), only this frame's column kernel is ordered
+ * behind the other frame. Every other entry point (downloads, sync, plain updates, uploads, ...) first orders the
+ * context's stream behind both lanes -- ocean_join does only that -- so results are those of the same calls made
+ * through ocean_update_tiles, bit for bit; a caller that consumes the maps on its own stream calls ocean_join first.
+ * FUSED pipeline, single-buffered contexts. */
+OCEAN_API int  ocean_update_overlapped(ocean_ctx* ctx, float time, uint32_t first_tile, uint32_t count);
+/* Enqueue, on the context's stream, a wait for the frames in flight on the lanes (no host blocking). */
+OCEAN_API int  ocean_join(ocean_ctx* ctx);
 /* Enqueue `n_frames` consecutive updates at times t0 + i*dt (host loop inside the library). */
 OCEAN_API int  ocean_update_sequence(ocean_ctx* ctx, float t0, float dt, uint32_t n_frames);
 

@@ -266,3 +266,72 @@ def test_split_launches_are_bit_identical():
         sums.append(json.loads(r.stdout.strip().splitlines()[-1]))
     assert sums[0] == sums[1]
     del data
+
+
+def test_overlapped_updates_match_plain_updates_bit_for_bit():
+    """ocean_update_overlapped: frames of different tiles in flight on two lanes; same maps as ocean_update_tiles,
+    also when ranges collide, when plain updates / uploads / read-backs are interleaved, and over many frames."""
+    n, tiles = 512, 4
+    data = [synthetic_tile(n, g + 80) for g in range(tiles)]
+    rng = np.random.default_rng(5)
+    plan = []                                        # (kind, time, first, count)
+    for f in range(120):
+        first = int(rng.integers(0, tiles))
+        count = 1 if f % 3 else int(rng.integers(1, tiles - first + 1))
+        plan.append(("plain" if f % 17 == 16 else "lane", 0.05 * f, first, count))
+    results = []
+    for mode in ("plain", "overlapped"):
+        with Ocean(n, 1000.0, n_tiles=tiles) as o:
+            for i, (h0, w) in enumerate(data):
+                o.set_spectrum(i, h0, w)
+            o.update(0.0)
+            trace = []
+            for step, (kind, t, first, count) in enumerate(plan):
+                if mode == "plain" or kind == "plain":
+                    o.update_tiles(t, first, count)
+                else:
+                    o.update_overlapped(t, first, count)
+                if step % 11 == 10:
+                    trace.append(o.output_checksums().copy())          # joins the lanes
+                if step == 60:
+                    o.set_spectrum(1, *data[3])                         # an upload in between: the lanes must see it
+            trace.append(o.output_checksums().copy())
+            trace.append(np.frombuffer(o.read_back(2).tobytes(), np.uint32).astype(np.uint64).sum())
+            results.append(trace)
+    for a, b in zip(*results):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_overlapped_single_tile_rotation_is_faster_or_equal_and_correct(oracle):
+    n, tiles = 1024, 8
+    with Ocean(n, 1000.0, n_tiles=tiles) as o:
+        for i in range(tiles):
+            o.generate_spectrum(i, 77, stream_id=i)
+        for f in range(64):
+            o.update_overlapped(0.016 * f, f % tiles, 1)
+        h0, w = o.get_spectrum(7)
+        out = o.read_back(7)                                            # tile 7 was last updated at frame 63
+    assert max(max_rel_err(out, oracle.frame(h0, w, 0.016 * 63, n, prec="f64"))) <= TOL
+
+
+def test_overlapped_same_tiles_every_frame_matches_plain():
+    """All tiles updated every frame through the lanes (the column kernel of frame n+1 is ordered behind frame n,
+    the row kernel is not): per-frame results must equal the plain sequence."""
+    n, tiles, frames = 1024, 3, 40
+    data = [synthetic_tile(n, g + 90) for g in range(tiles)]
+    with Ocean(n, 1000.0, n_tiles=tiles) as o:
+        for i, (h0, w) in enumerate(data):
+            o.set_spectrum(i, h0, w)
+        plain = {}
+        for f in range(frames):
+            o.update(0.016 * f)
+            if f % 7 == 6 or f == frames - 1:
+                plain[f] = o.output_checksums().copy()
+        got = {}
+        for f in range(frames):
+            o.update_overlapped(0.016 * f)                      # no host synchronisation between the frames
+            if f % 7 == 6 or f == frames - 1:
+                got[f] = o.output_checksums().copy()
+        assert got.keys() == plain.keys()
+        for f in got:
+            np.testing.assert_array_equal(got[f], plain[f])
