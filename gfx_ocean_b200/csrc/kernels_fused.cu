@@ -69,6 +69,8 @@ struct LineCfg {
     static constexpr int LINE = ((pad(N - 1) + 1 - 2 + 15) / 16) * 16 + 2;
     // same for 4 lines x 4 rows per half-warp (the packed height columns of k_cols): == 4 (mod 16)
     static constexpr int LINE_H = ((pad(N - 1) + 1 - 4 + 15) / 16) * 16 + 4;
+    // and for 2 lines x 8 rows per half-warp (4-column strips: two packed height columns): == 8 (mod 16)
+    static constexpr int LINE_H2 = ((pad(N - 1) + 1 - 8 + 15) / 16) * 16 + 8;
 };
 
 // Passes 2 (and 3) of a line held in shared memory at line[pad(p)], for the three-pass factorisation.
@@ -100,6 +102,40 @@ __device__ __forceinline__ void line_passes_23(float2* line, int t, const float2
         RegFft<R3>::run(w);
 #pragma unroll
         for (int n3 = 0; n3 < R3; ++n3) out(n1 + R1 * n2 + R1 * R2 * n3, w[n3]);
+    }
+}
+
+// The three-pass factorisation with R3 = 2 (N = 2048), closing radix-2 as a WARP-SHUFFLE butterfly. Threads t = 2g and
+// 2g + 1 of a line (LANE_XOR lanes apart in their warp) hold, after pass 2, the two k3 inputs of every (n1 = g, n2)
+// butterfly. Instead of a second trip through shared memory (32 stores + barrier + 32 loads per thread) each lane sends
+// its partner the half it does not finish itself: lane k3 = 0 completes the even n2, lane k3 = 1 the odd n2 -- 16
+// complex shuffles per thread and no barrier. Same arithmetic as line_passes_23 (a + b, a - b), bit for bit.
+// ld(p) reads position p of the pass-1 output; loaded() runs once the thread holds its inputs (the line may then be
+// released); out(n, value) receives natural-order results. Every lane of the warp must take part.
+#ifndef OCEAN_SHFL_RADIX2
+#define OCEAN_SHFL_RADIX2 1
+#endif
+template <class Cfg, int LANE_XOR, class Ld, class Loaded, class Out>
+__device__ __forceinline__ void line_pass2_shfl(int t, const float2* __restrict__ tw2, Ld ld, Loaded loaded, Out out)
+{
+    constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2;
+    static_assert(Cfg::R3 == 2 && Cfg::SUB2 == 1 && R2 % 2 == 0, "one pass-2 sub-transform per thread, lane pairs close the line");
+    const int g = t >> 1, k3 = t & 1;
+    float2 u[R2];
+#pragma unroll
+    for (int k = 0; k < R2; ++k) u[k] = ld(g * T + k * 2 + k3);
+    loaded();
+    RegFft<R2>::run(u);
+#pragma unroll
+    for (int n2 = 1; n2 < R2; ++n2) u[n2] = cmul_tw(u[n2], tw2[n2 * 2 + k3]);
+#pragma unroll
+    for (int i = 0; i < R2 / 2; ++i) {
+        const float2 send = k3 ? u[2 * i] : u[2 * i + 1];
+        const float2 recv = make_float2(__shfl_xor_sync(0xffffffffu, send.x, LANE_XOR), __shfl_xor_sync(0xffffffffu, send.y, LANE_XOR));
+        const float2 a = k3 ? recv : u[2 * i], b = k3 ? u[2 * i + 1] : recv;        // the k3 = 0 / k3 = 1 input at n2 = 2 i + k3
+        const int n = g + R1 * (2 * i + k3);
+        out(n, make_float2(a.x + b.x, a.y + b.y));
+        out(n + R1 * R2, make_float2(a.x - b.x, a.y - b.y));
     }
 }
 
@@ -168,10 +204,14 @@ __device__ __forceinline__ void rows_line_finish(float2 (&v)[LineCfg<N, P>::R1],
     else dst = gh + IL::row_off(j);
     const long strip_stride = seq == 2 ? IL::H_STRIP : IL::P_STRIP;
     if constexpr (Cfg::R3 > 1) {
-        line_passes_23<Cfg>(line, k2, tw_g + N, [] { __syncthreads(); }, [&](int n, float2 val) {
+        auto store = [&](int n, float2 val) {
             const uint32_t col = mirrored ? ((N - n) & (N - 1)) : n;
             dst[long(col / C) * strip_stride + col % C] = val;
-        });
+        };
+        if constexpr (Cfg::R3 == 2 && OCEAN_SHFL_RADIX2)      // k2 = tid % T with T a multiple of 32: the pair sits in lanes 2g, 2g + 1
+            line_pass2_shfl<Cfg, 1>(k2, tw_g + N, [&](int p) { return line[Cfg::pad(p)]; }, [] {}, store);
+        else
+            line_passes_23<Cfg>(line, k2, tw_g + N, [] { __syncthreads(); }, store);
         return;
     }
     const long step = (mirrored ? -long(R1 / C) : long(R1 / C)) * strip_stride;
@@ -386,11 +426,20 @@ __device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1
 #define OCEAN_ROWS_T_PREFETCH 0
 #endif
 #ifndef OCEAN_ROWS_T_UNROLL
-#define OCEAN_ROWS_T_UNROLL 2           // point pairs of phase A in flight per thread
+#define OCEAN_ROWS_T_UNROLL 3           // point pairs of phase A in flight per thread (2 -> 3: +1 % at 1024, same box)
+#endif
+#ifndef OCEAN_ROWS_T_SPLIT_BAR
+#define OCEAN_ROWS_T_SPLIT_BAR 1        // +1.2 % at 1024, +2.8 % at 2048 (same box)
+#endif
+// OCEAN_ROWS_T_OMEGA_LDG = 1 (A/B builds): omega is not staged in shared memory; every thread fetches the values of its
+// own points with read-only global loads issued before it waits for the bulk copies (they stay in registers through
+// phase A). The slots shrink from 20 to 16 KB per row at N = 1024, which makes room for a sixth block per SM.
+#ifndef OCEAN_ROWS_T_OMEGA_LDG
+#define OCEAN_ROWS_T_OMEGA_LDG 0
 #endif
 template <int N>
 struct RowSlot {
-    static constexpr uint32_t REV_OFF = 8u * (N + 2), OM_OFF = 16u * (N + 2), BYTES = OM_OFF + 4u * N;
+    static constexpr uint32_t REV_OFF = 8u * (N + 2), OM_OFF = 16u * (N + 2), BYTES = OM_OFF + (OCEAN_ROWS_T_OMEGA_LDG ? 0u : 4u * N);
     static_assert(REV_OFF % 16 == 0 && BYTES % 16 == 0, "bulk copies need 16-byte granules");
     unsigned char* base;
     __device__ __forceinline__ float2* fwd() const { return reinterpret_cast<float2*>(base); }
@@ -435,19 +484,38 @@ k_rows_t(const float2* __restrict__ h0_all, const float* __restrict__ omega_all,
         const uint32_t jp = blockIdx.x * PAIRS + (slot >> 1);            // pair index, 0 = the self-paired rows 0, N/2
         return jp == 0 ? ((slot & 1) ? N / 2 : 0) : ((slot & 1) ? N - jp : jp);
     };
+    // OCEAN_ROWS_T_SPLIT_BAR = 1: one mbarrier per row, so that phase A of the first row starts while the second is in flight
+    constexpr int NBAR = OCEAN_ROWS_T_SPLIT_BAR ? NROWS : 1;
     if (tid == 0) {
-        ptx::mbar_init(bar, 1);
+        for (int i = 0; i < NBAR; ++i) ptx::mbar_init(bar + i, 1);
         ptx::fence_mbar_init();
         // h0 / omega are never written by a frame kernel: no griddepcontrol.wait before reading them
-        ptx::mbar_arrive_expect_tx(bar, NROWS * (2 * N * sizeof(float2) + N * sizeof(float)));
+        constexpr uint32_t ROW_TX = 2 * N * sizeof(float2) + (OCEAN_ROWS_T_OMEGA_LDG ? 0 : N * sizeof(float));
+        for (int i = 0; i < NBAR; ++i) ptx::mbar_arrive_expect_tx(bar + i, (NROWS / NBAR) * ROW_TX);
         for (int slot = 0; slot < NROWS; ++slot) {
             const uint32_t r = row_of(slot);
             const Slot sl{smem_raw + slot * Slot::BYTES};
-            ptx::bulk_g2s(sl.fwd(), h0 + size_t(r) * N, N * sizeof(float2), bar);                 // propagate.comp:43
-            ptx::bulk_g2s(sl.rev(), h0 + size_t(N - 1 - r) * N, N * sizeof(float2), bar);         // :48, read reversed below
-            ptx::bulk_g2s(sl.om(), omega + size_t(r) * N, N * sizeof(float), bar);
+            uint64_t* b = bar + (NBAR > 1 ? slot : 0);
+            ptx::bulk_g2s(sl.fwd(), h0 + size_t(r) * N, N * sizeof(float2), b);                 // propagate.comp:43
+            ptx::bulk_g2s(sl.rev(), h0 + size_t(N - 1 - r) * N, N * sizeof(float2), b);         // :48, read reversed below
+#if !OCEAN_ROWS_T_OMEGA_LDG
+            ptx::bulk_g2s(sl.om(), omega + size_t(r) * N, N * sizeof(float), b);
+#endif
         }
     }
+#if OCEAN_ROWS_T_OMEGA_LDG
+    constexpr int ITER_A = (N / 2 + NT - 1) / NT;
+    float2 wreg[NROWS][ITER_A];
+#pragma unroll
+    for (int slot = 0; slot < NROWS; ++slot) {
+        const float2* __restrict__ wrow = reinterpret_cast<const float2*>(omega + size_t(row_of(slot)) * N);
+#pragma unroll
+        for (int it = 0; it < ITER_A; ++it) {
+            const int i = tid + it * NT;
+            wreg[slot][it] = i < N / 2 ? __ldg(wrow + i) : make_float2(0.f, 0.f);
+        }
+    }
+#endif
 #if OCEAN_ROWS_T_PREFETCH > 0
     {
         // While this block waits for its own rows, pull the rows of the block that will run about one wave later from
@@ -471,34 +539,106 @@ k_rows_t(const float2* __restrict__ h0_all, const float* __restrict__ omega_all,
     }
 #endif
     __syncthreads();                      // the barrier is initialised before anyone polls it
-    ptx::mbar_wait(bar, 0);
+    if constexpr (NBAR == 1) ptx::mbar_wait(bar, 0);
 
-    // ---- phase A: propagate.comp, in place. A thread takes point pairs x = 2 (tid + k NT).
-#pragma unroll 1
-    for (int slot = 0; slot < NROWS; ++slot) {
-        const Slot sl{smem_raw + slot * Slot::BYTES};
-        const float ky = __ldg(kx_g + row_of(slot));
+    // ---- phase A: propagate.comp, in place. A thread takes point pairs x = 2 (tid + k NT), U pairs (2 U points) at a
+    // time: all loads first, then every point's phase and MUFU sincos in straight-line code -- the 2 U dependent
+    // chains (multiply, reduce, MUFU, rotate) interleave -- and ONE test per batch for the arguments beyond the fast
+    // path's range (|omega t| > 1e5, i.e. t of the order of hours), which then takes libdevice's Payne-Hanek sincos.
+    // A test per point, as propagate_point_fast has it, fences every chain between two reconvergence points and
+    // leaves each warp with one ~70-cycle dependent chain at a time. Same arithmetic per point, bit for bit.
+    auto phase_a_batch = [&](const Slot& sl, float ky, const int (&idx)[OCEAN_ROWS_T_UNROLL], const float2 (&w)[OCEAN_ROWS_T_UNROLL]) {
+        constexpr int U = OCEAN_ROWS_T_UNROLL;
         float4* F4 = reinterpret_cast<float4*>(sl.fwd());
         float4* R4 = reinterpret_cast<float4*>(sl.rev());
-        const float2* W2 = reinterpret_cast<const float2*>(sl.om());
         const float2* __restrict__ pk = reinterpret_cast<const float2*>(kx_g);
-        constexpr int kUnrollA = OCEAN_ROWS_T_UNROLL;
-#pragma unroll kUnrollA
-        for (int i = tid; i < N / 2; i += NT) {
-            const float2 w = W2[i];
-            const float4 a = F4[i], b = R4[N / 2 - 1 - i];     // b.zw is the partner of x = 2 i, b.xy the partner of x + 1
-            const float2 kx = __ldg(pk + i);
-            const float2 h_0 = propagate_point_fast(make_float2(a.x, a.y), make_float2(b.z, b.w), w.x, time);
-            const float2 h_1 = propagate_point_fast(make_float2(a.z, a.w), make_float2(b.x, b.y), w.y, time);
-            const float2 k_0 = unit_wave_vector_fast(kx.x, ky);
-            const float2 k_1 = unit_wave_vector_fast(kx.y, ky);
-            F4[i] = make_float4(h_0.x, h_0.y, h_1.x, h_1.y);                 // H[x], H[x + 1]
-            R4[N / 2 - 1 - i] = make_float4(k_1.x, k_1.y, k_0.x, k_0.y);     // K[x + 1] at REV[N-2-x], K[x] at REV[N-1-x]
-            if (i == 0) {
-                sl.fwd()[N] = h_0;                                           // H[N] = H[0]
-                sl.rev()[-1] = k_0;                                          // K[N] = K[0] (the spare slot before REV)
+        float4 a[U], b[U];
+        float2 kx[U];
+        float ph[2 * U], sn[2 * U], cs[2 * U];
+        float worst = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool on = idx[u] < N / 2;
+            const int i = on ? idx[u] : 0;
+            a[u] = F4[i];
+            b[u] = R4[N / 2 - 1 - i];                    // b.zw is the partner of x = 2 i, b.xy the partner of x + 1
+            kx[u] = __ldg(pk + i);
+            ph[2 * u] = on ? __fmul_rn(w[u].x, time) : 0.f;
+            ph[2 * u + 1] = on ? __fmul_rn(w[u].y, time) : 0.f;
+            worst = fmaxf(worst, fmaxf(fabsf(ph[2 * u]), fabsf(ph[2 * u + 1])));
+        }
+#pragma unroll
+        for (int q = 0; q < 2 * U; ++q) sincos_in_range(ph[q], sn[q], cs[q]);
+        if (!(worst <= 1.0e5f)) {                        // also taken for NaN phases, like sincos_full's test
+#pragma unroll
+            for (int q = 0; q < 2 * U; ++q)
+                if (!(fabsf(ph[q]) <= 1.0e5f)) {
+                    const float2 sc = sincos_huge(ph[q]);
+                    sn[q] = sc.x;
+                    cs[q] = sc.y;
+                }
+        }
+        float2 h_0[U], h_1[U], k_0[U], k_1[U];           // computed for every slot of the batch (an idle slot re-does pair 0), stored by the live ones
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            h_0[u] = propagate_point_sc(make_float2(a[u].x, a[u].y), make_float2(b[u].z, b[u].w), sn[2 * u], cs[2 * u]);
+            h_1[u] = propagate_point_sc(make_float2(a[u].z, a[u].w), make_float2(b[u].x, b[u].y), sn[2 * u + 1], cs[2 * u + 1]);
+            k_0[u] = unit_wave_vector_fast(kx[u].x, ky);
+            k_1[u] = unit_wave_vector_fast(kx[u].y, ky);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = idx[u];
+            if (i < N / 2) {
+                F4[i] = make_float4(h_0[u].x, h_0[u].y, h_1[u].x, h_1[u].y);             // H[x], H[x + 1]
+                R4[N / 2 - 1 - i] = make_float4(k_1[u].x, k_1[u].y, k_0[u].x, k_0[u].y); // K[x + 1] at REV[N-2-x], K[x] at REV[N-1-x]
+                if (i == 0) {
+                    sl.fwd()[N] = h_0[u];                                                // H[N] = H[0]
+                    sl.rev()[-1] = k_0[u];                                               // K[N] = K[0] (the spare slot before REV)
+                }
             }
         }
+    };
+    {
+        constexpr int U = OCEAN_ROWS_T_UNROLL;
+#if OCEAN_ROWS_T_OMEGA_LDG
+#pragma unroll
+        for (int slot = 0; slot < NROWS; ++slot) {
+            const Slot sl{smem_raw + slot * Slot::BYTES};
+            const float ky = __ldg(kx_g + row_of(slot));
+            if constexpr (NBAR > 1) ptx::mbar_wait(bar + slot, 0);
+#pragma unroll
+            for (int it = 0; it < ITER_A; it += U) {
+                int idx[U];
+                float2 w[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    idx[u] = it + u < ITER_A ? tid + (it + u) * NT : N;
+                    w[u] = wreg[slot][it + u < ITER_A ? it + u : 0];
+                }
+                phase_a_batch(sl, ky, idx, w);
+            }
+        }
+#else
+#pragma unroll 1
+        for (int slot = 0; slot < NROWS; ++slot) {
+            const Slot sl{smem_raw + slot * Slot::BYTES};
+            const float ky = __ldg(kx_g + row_of(slot));
+            const float2* W2 = reinterpret_cast<const float2*>(sl.om());
+            if constexpr (NBAR > 1) ptx::mbar_wait(bar + slot, 0);
+#pragma unroll 1
+            for (int i0 = tid; i0 < N / 2; i0 += U * NT) {
+                int idx[U];
+                float2 w[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    idx[u] = i0 + u * NT;
+                    w[u] = W2[idx[u] < N / 2 ? idx[u] : 0];
+                }
+                phase_a_batch(sl, ky, idx, w);
+            }
+        }
+#endif
     }
     __syncthreads();
 
@@ -918,8 +1058,11 @@ struct ColsCfg {
     static constexpr int NTHREADS = NTP + NTH + 32;   // + one producer warp
     static constexpr uint32_t P_BYTES = IL::P_STRIP * sizeof(float2);
     static constexpr uint32_t H_BYTES = IL::H_STRIP * sizeof(float2);
-    static constexpr uint32_t XH_BYTES = HC * Line::LINE_H * sizeof(float2);
-    static_assert(sizeof(float) * N * C <= P_BYTES, "height results must fit in a drained GP buffer");
+    static constexpr int LINE_H = HC == 2 ? Line::LINE_H2 : Line::LINE_H;   // line pitch of XH: conflict-free for HC lines per half-warp
+    static constexpr uint32_t XH_BYTES = HC * LINE_H * sizeof(float2);
+    // row of the height results HR (parked in a drained GP buffer); the shuffle-closed three-pass lines pad it
+    __host__ __device__ static constexpr int hr_row(int m) { return (Line::R3 == 2 && OCEAN_SHFL_RADIX2) ? m + 4 * (m / 32) : m; }
+    static_assert(sizeof(float) * (hr_row(N - 1) + 1) * C <= P_BYTES, "height results must fit in a drained GP buffer");
     static_assert(P_BYTES % 16 == 0 && H_BYTES % 16 == 0 && XH_BYTES % 16 == 0, "bulk copies need 16-byte granules");
     static constexpr uint32_t TW_BYTES = (N + Line::T) * sizeof(float2);   // pass-1 twiddles [R1][T] + pass-2 twiddles [R2][R3]
     static constexpr size_t SMEM = 2 * size_t(P_BYTES) + H_BYTES + XH_BYTES + TW_BYTES + 10 * sizeof(uint64_t);
@@ -944,7 +1087,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
     using CC = ColsCfg<N, P, C>;
     using Cfg = typename CC::Line;
     using IL = typename CC::IL;
-    constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2, R3 = Cfg::R3, LINE = Cfg::LINE_H;
+    constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2, R3 = Cfg::R3, LINE = CC::LINE_H;
     constexpr int NTP = CC::NTP, NTH = CC::NTH, HC = CC::HC;
     constexpr int STRIPS = N / C;
 
@@ -1084,6 +1227,24 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                     }
                 }
             } else {
+                if constexpr (R3 == 2 && OCEAN_SHFL_RADIX2) {
+                    // pass 2 in registers, closing radix-2 by shuffle between the threads k2 = 2g, 2g + 1 (HC lanes apart);
+                    // the results wait in registers for the packed warps to drain PB
+                    float2 r[R1];
+                    int i = 0;
+                    line_pass2_shfl<Cfg, HC>(k2, TW + N, [&](int p) { return line[Cfg::pad(p)]; },
+                                             [&] { ptx::named_bar_sync<2, NTH>(); },     // XH drained: the next item may overwrite it
+                                             [&](int, float2 val) { r[i++] = val; });
+                    ptx::mbar_wait(drainedP + b, (it >> 1) & 1);
+                    // rows m = g + 32 k3 + 64 q (+ N/2): HR rows get 4 pad rows per 32 (CC::hr_row) so that the two k3 halves
+                    // of a half-warp fall into different banks
+                    const int m0 = (k2 >> 1) + R1 * (k2 & 1);
+#pragma unroll
+                    for (int q = 0; q < R1 / 2; ++q) {
+                        *reinterpret_cast<float2*>(HR + CC::hr_row(m0 + 2 * R1 * q) * C + 2 * pc) = r[2 * q];
+                        *reinterpret_cast<float2*>(HR + CC::hr_row(m0 + 2 * R1 * q + R1 * R2) * C + 2 * pc) = r[2 * q + 1];
+                    }
+                } else {
                 // pass 2 in XH, then wait for the packed warps before pass 3 streams its results into HR
                 bool waited = false;
                 line_passes_23<Cfg>(line, k2, TW + N, [&] {
@@ -1093,6 +1254,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                 }, [&](int m, float2 val) { *reinterpret_cast<float2*>(HR + m * C + 2 * pc) = val; });
                 (void)waited;
                 ptx::named_bar_sync<2, NTH>();                          // XH drained: the next item may overwrite it
+                }
             }
             ptx::fence_proxy_async();          // HR lives in PB[b], which the async proxy refills two items later
             ptx::mbar_arrive(hrReady);
@@ -1157,6 +1319,22 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                     }
                 }
             } else {
+                if constexpr (R3 == 2 && OCEAN_SHFL_RADIX2) {
+                    // pass 2 in registers, closing radix-2 by shuffle between the threads k2 = 2g, 2g + 1 (C lanes apart)
+                    float2 r[R1];
+                    int i = 0;
+                    line_pass2_shfl<Cfg, C>(k2, TW + N, [&](int p) { return PB[IL::row_off(p) + c]; },
+                                            [&] { ptx::mbar_arrive(drainedP + b); },
+                                            [&](int, float2 val) { r[i++] = val; });
+                    ptx::mbar_wait(hrReady, it & 1);
+                    const uint32_t m0 = (k2 >> 1) + R1 * (k2 & 1);
+#pragma unroll
+                    for (int q = 0; q < R1 / 2; ++q) {
+                        const uint32_t ma = m0 + 2 * R1 * q, mb = ma + R1 * R2;
+                        emit(ma, r[2 * q].x, HR[CC::hr_row(ma) * C + c], r[2 * q].y);
+                        emit(mb, r[2 * q + 1].x, HR[CC::hr_row(mb) * C + c], r[2 * q + 1].y);
+                    }
+                } else {
                 // pass 2 in place, pass 3 into registers, then the same exchange with the height warps
                 const int g = k2 / R3, k3 = k2 % R3;
 #pragma unroll
@@ -1189,6 +1367,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                         const uint32_t m = n1 + R1 * n2 + R1 * R2 * n3;
                         emit(m, w[i][n3].x, HR[m * C + c], w[i][n3].y);
                     }
+                }
                 }
             }
             ptx::fence_proxy_async();          // generic-proxy accesses to PB[b] precede the next bulk copy into it
@@ -1234,7 +1413,7 @@ struct Launch {
     using IL = typename CC::IL;
     using RC = RowsCfg<N, P, PPAIRS, C, GROUPS, SLOTS>;
     using RC1 = RowsCfg<N, P, PPAIRS, C, 1, 0>;            // one unit per block, hardware-scheduled
-    static constexpr size_t smem_rows_t = size_t(2 * PAIRS) * RowSlot<N>::BYTES + 16;
+    static constexpr size_t smem_rows_t = size_t(2 * PAIRS) * RowSlot<N>::BYTES + 16 * PAIRS;   // + one mbarrier per row
     static constexpr size_t smem_rows = sizeof(float4) * 2 * PAIRS * (N + 1);
 
     static cudaError_t prepare(FusedPlan* p)
@@ -1362,7 +1541,10 @@ using L512 = Launch<512, 32, OCEAN_ROWS_PAIRS_512, 8, OCEAN_ROWS_MINB_512, 2, OC
 #ifndef OCEAN_ROWS_SLOTS_2048
 #define OCEAN_ROWS_SLOTS_2048 1
 #endif
-using L2048 = Launch<2048, 32, 1, 4, 2, 1, OCEAN_ROWS_GROUPS_2048, OCEAN_ROWS_SLOTS_2048>;   // three-pass lines (32 x 32 x 2), strips of 4 columns
+#ifndef OCEAN_ROWS_MINB_2048
+#define OCEAN_ROWS_MINB_2048 2
+#endif
+using L2048 = Launch<2048, 32, 1, 4, OCEAN_ROWS_MINB_2048, 1, OCEAN_ROWS_GROUPS_2048, OCEAN_ROWS_SLOTS_2048>;   // three-pass lines (32 x 32 x 2), strips of 4 columns
 // k_rows at N=1024: 5 blocks/SM (128 registers, no spills) measured faster than 6 blocks/SM at 96 registers
 // (68 vs 76 us per 8 tiles); overridable for A/B builds (scripts/ab_build.sh)
 #ifndef OCEAN_ROWS_PAIRS_1024

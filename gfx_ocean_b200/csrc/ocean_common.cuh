@@ -105,18 +105,30 @@ __device__ __forceinline__ void sincos_mufu(float x, float& sn, float& cs)
     cs = __cosf(r);
 }
 
-__device__ __forceinline__ void sincos_full(float x, float& sn, float& cs)
+// the fast path of sincos_full, valid for |x| <= 1e5
+__device__ __forceinline__ void sincos_in_range(float x, float& sn, float& cs)
 {
 #ifdef OCEAN_SINCOS_POLY
-    if (fabsf(x) <= 1.0e5f) sincos_reduced(x, sn, cs);
+    sincos_reduced(x, sn, cs);
 #else
-    if (fabsf(x) <= 1.0e5f) sincos_mufu(x, sn, cs);
+    sincos_mufu(x, sn, cs);
 #endif
+}
+
+__device__ __forceinline__ void sincos_full(float x, float& sn, float& cs)
+{
+    if (fabsf(x) <= 1.0e5f) sincos_in_range(x, sn, cs);
     else {
         const float2 sc = sincos_huge(x);
         sn = sc.x;
         cs = sc.y;
     }
+}
+
+// propagate.comp:55-62 with the sine and cosine of the phase given.
+__device__ __forceinline__ float2 propagate_point_sc(float2 a, float2 b, float s, float c)
+{
+    return make_float2((a.x + b.x) * c - (a.y - b.y) * s, (a.y + b.y) * c + (a.x - b.x) * s);
 }
 
 // Same as propagate_point with the sincos above.

@@ -1,12 +1,12 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8 > gpurun_out/r2q_pytest.log
-for tool in racecheck memcheck; do echo "== $tool overlapped"; timeout 500 compute-sanitizer --tool $tool --print-limit 4 python - <<'PY' 2>&1 | grep -E "SUMMARY|Error|sums" | head
-import sys; sys.path.insert(0, '.')
-from gfx_ocean_b200 import Ocean
-with Ocean(512, 1000.0, n_tiles=3) as o:
-    for i in range(3): o.generate_spectrum(i, 7, stream_id=i)
-    for f in range(6): o.update_overlapped(0.1 * f)
-    for f in range(6): o.update_overlapped(0.1 * f, f % 3, 1)
-    print("sums", [hex(int(s)) for s in o.output_checksums()])
-PY
-done > gpurun_out/r2q_sanitizer.log 2>&1
+V=$PWD/gfx_ocean_b200/variants
+for lib in default w2048; do
+  if [ $lib = default ]; then unset OCEAN_B200_LIB; else export OCEAN_B200_LIB=$V/libocean_b200.$lib.so; fi
+  python scripts/san_target.py 2048 2 3 > gpurun_out/r2w_sums_$lib.log 2>&1
+  for rep in 1 2; do
+  timeout 300 python bench.py --resolution 2048 --tiles 2 --steps 300 --no-extras --no-cpu-baseline > gpurun_out/r2w_bench2048_${lib}_$rep.json 2>> gpurun_out/r2w_bench_$lib.err
+  done
+done
+unset OCEAN_B200_LIB
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r2w_pytest.log
+echo done
