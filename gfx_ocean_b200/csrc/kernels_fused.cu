@@ -560,8 +560,9 @@ k_rows_t(const float2* __restrict__ h0_all, const float* __restrict__ omega_all,
         for (int u = 0; u < U; ++u) {
             const bool on = idx[u] < N / 2;
             const int i = on ? idx[u] : 0;
-            a[u] = F4[i];
-            b[u] = R4[N / 2 - 1 - i];                    // b.zw is the partner of x = 2 i, b.xy the partner of x + 1
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            a[u] = on ? F4[i] : zero;                    // (an idle slot of the batch reads nothing: predicated loads)
+            b[u] = on ? R4[N / 2 - 1 - i] : zero;        // b.zw is the partner of x = 2 i, b.xy the partner of x + 1
             kx[u] = __ldg(pk + i);
             ph[2 * u] = on ? __fmul_rn(w[u].x, time) : 0.f;
             ph[2 * u + 1] = on ? __fmul_rn(w[u].y, time) : 0.f;
@@ -578,7 +579,7 @@ k_rows_t(const float2* __restrict__ h0_all, const float* __restrict__ omega_all,
                     cs[q] = sc.y;
                 }
         }
-        float2 h_0[U], h_1[U], k_0[U], k_1[U];           // computed for every slot of the batch (an idle slot re-does pair 0), stored by the live ones
+        float2 h_0[U], h_1[U], k_0[U], k_1[U];           // computed for every slot of the batch (an idle slot works on zeros), stored by the live ones
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             h_0[u] = propagate_point_sc(make_float2(a[u].x, a[u].y), make_float2(b[u].z, b[u].w), sn[2 * u], cs[2 * u]);

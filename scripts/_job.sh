@@ -1,12 +1,8 @@
 mkdir -p gpurun_out
-V=$PWD/gfx_ocean_b200/variants
-for lib in default w2048; do
-  if [ $lib = default ]; then unset OCEAN_B200_LIB; else export OCEAN_B200_LIB=$V/libocean_b200.$lib.so; fi
-  python scripts/san_target.py 2048 2 3 > gpurun_out/r2w_sums_$lib.log 2>&1
-  for rep in 1 2; do
-  timeout 300 python bench.py --resolution 2048 --tiles 2 --steps 300 --no-extras --no-cpu-baseline > gpurun_out/r2w_bench2048_${lib}_$rep.json 2>> gpurun_out/r2w_bench_$lib.err
+for tool in racecheck; do
+  for cfg in "1024 4 2" "512 3 3" "2048 1 2" "512 3 6 overlapped" "256 2 3" "64 2 3"; do
+    echo "== compute-sanitizer --tool $tool python scripts/san_target.py $cfg"
+    timeout 600 compute-sanitizer --tool $tool --print-limit 6 python scripts/san_target.py $cfg 2>&1 | grep -E "SUMMARY|Error:|access at|checksums|hazards" | cut -c1-330 | head -14
   done
-done
-unset OCEAN_B200_LIB
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r2w_pytest.log
+done > gpurun_out/r2x_racecheck.log 2>&1
 echo done
