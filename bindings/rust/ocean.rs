@@ -161,6 +161,14 @@ impl Ocean {
         if rc != 0 { Err(Self::err(self.ctx, rc)) } else { Ok(()) }
     }
 
+    /// `update` with frames in flight (src/lib.rs:86): consecutive calls alternate between two internal lanes, so the
+    /// row kernel of one frame runs beside the column kernel of the previous one. Same maps, bit for bit; every
+    /// other call (read_back, output, ...) first orders the context's stream behind both lanes.
+    pub fn update_overlapped(&mut self, time: f32) -> Result<(), OceanError> {
+        let rc = unsafe { ocean_update_overlapped(self.ctx, time, 0, 1) };
+        if rc != 0 { Err(Self::err(self.ctx, rc)) } else { Ok(()) }
+    }
+
     /// Device pointer to N*N RGBA32F texels (dx, height, dz, 0), row-major [y][x]; stable for the
     /// lifetime of `self`. Import it as the displacement texture (external memory), or `read_back`.
     pub fn output(&self) -> Result<*const [f32; 4], OceanError> {

@@ -61,24 +61,26 @@ __host__ __device__ constexpr double sin2pi(long k, long n) { return cos2pi(4 * 
 // OCEAN_FFT_PACKED (device code, sm_100+): 1 = the twiddle-free butterflies (w = 1: 31 of the 80 butterflies of a
 // 32-point transform) use the packed add.rn.f32x2 / fma.rn.f32x2 on the (re, im) register pair -- two instructions
 // instead of four; 2 = the general butterflies use fma.rn.f32x2 as well (three packed FMAs + the swapped operand).
-// 0 = scalar (default). Measured on B200 (1024^2 x 8 tiles): 80.2 k / 79.2 k / 79.4 k frames/s for 0 / 1 / 2 -- the
-// static instruction count of k_rows_t drops 2880 -> 2800 -> 2640 but the kernels are latency bound, not issue bound,
-// and the scalar form keeps its twiddles as FFMA immediates.
+// 0 = scalar. Measured on B200 (same box, 0 / 1 / 2): 1024^2 x 8 tiles 83.1 k / 82.4 k / 82.8 k frames/s (single-tile
+// frames 13.2 / 13.1 / 12.9 us), 512^2 312.9 k / 312.5 k / 313.2 k, 2048^2 16.4 k / 17.0 k / 17.0 k -- the static
+// instruction count of k_rows_t drops 2880 -> 2800 -> 2640 but the two-pass kernels are latency bound, not issue bound,
+// and the scalar form keeps its twiddles as FFMA immediates. Level 1 is bit-identical to scalar, level 2 rounds differently.
+// The macro is the default of the PK template parameter; the line configurations pick level 1 for the three-pass
+// lines (N = 2048), see LineCfg::PK.
 #ifndef OCEAN_FFT_PACKED
 #define OCEAN_FFT_PACKED 0
 #endif
 
-template <int R, int K>
+template <int R, int K, int PK>
 __host__ __device__ __forceinline__ void dit_butterfly(const float2 e, const float2 o, float2& lo, float2& hi)
 {
-#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000 && OCEAN_FFT_PACKED >= 1
-    if constexpr (K == 0) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    if constexpr (K == 0 && PK >= 1) {
         lo = __fadd2_rn(e, o);
         hi = __ffma2_rn(o, make_float2(-1.0f, -1.0f), e);      // e - o, exact like a subtraction
         return;
     }
-#if OCEAN_FFT_PACKED >= 2
-    if constexpr (4 * K != R) {
+    if constexpr (4 * K != R && K != 0 && PK >= 2) {
         constexpr float wr = float(cos2pi(K, R));
         constexpr float wi = float(sin2pi(K, R));
         const float2 t = __ffma2_rn(make_float2(wr, wr), o, e);                        // e + wr o
@@ -86,7 +88,6 @@ __host__ __device__ __forceinline__ void dit_butterfly(const float2 e, const flo
         hi = __ffma2_rn(make_float2(2.0f, 2.0f), e, make_float2(-lo.x, -lo.y));        // 2e - lo
         return;
     }
-#endif
 #endif
     if constexpr (K == 0) {
         lo = make_float2(e.x + o.x, e.y + o.y);
@@ -104,13 +105,14 @@ __host__ __device__ __forceinline__ void dit_butterfly(const float2 e, const flo
     }
 }
 
-template <int R>
+// PK: packed level of the butterflies (see OCEAN_FFT_PACKED); the line configurations choose it per N (LineCfg::PK)
+template <int R, int PK = OCEAN_FFT_PACKED>
 struct RegFft {
     template <int... K>
     __host__ __device__ __forceinline__ static void combine(const float2 (&e)[R / 2], const float2 (&o)[R / 2],
                                                    float2 (&v)[R], std::integer_sequence<int, K...>)
     {
-        (dit_butterfly<R, K>(e[K], o[K], v[K], v[K + R / 2]), ...);
+        (dit_butterfly<R, K, PK>(e[K], o[K], v[K], v[K + R / 2]), ...);
     }
 
     __host__ __device__ __forceinline__ static void run(float2 (&v)[R])
@@ -121,14 +123,14 @@ struct RegFft {
             e[k] = v[2 * k];
             o[k] = v[2 * k + 1];
         }
-        RegFft<R / 2>::run(e);
-        RegFft<R / 2>::run(o);
+        RegFft<R / 2, PK>::run(e);
+        RegFft<R / 2, PK>::run(o);
         combine(e, o, v, std::make_integer_sequence<int, R / 2>{});
     }
 };
 
-template <>
-struct RegFft<1> {
+template <int PK>
+struct RegFft<1, PK> {
     __host__ __device__ __forceinline__ static void run(float2 (&)[1]) {}
 };
 

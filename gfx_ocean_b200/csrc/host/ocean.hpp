@@ -59,6 +59,9 @@ public:
     ~Ocean() { ocean_destroy(ctx_); }      // ::destroy(self, device)
 
     void update(float time) { check(ocean_update(ctx_, time)); }                 // asynchronous
+    // frames in flight (src/lib.rs:86): consecutive updates alternate between two internal lanes; same maps, bit for bit
+    void update_overlapped(float time) { check(ocean_update_overlapped(ctx_, time, 0, 1)); }
+    void join() { check(ocean_join(ctx_)); }   // order the context's stream behind the lanes (every other call does it too)
     void sync() { check(ocean_sync(ctx_)); }
     const float* output() const                                                   // N*N*4 floats on the device
     {

@@ -50,6 +50,9 @@ __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcon
 //   pass 2  radix R2 (stride R3), twiddle w_T^(n2 k3)            [P / R2 sub-transforms per thread]
 //   pass 3  radix R3 (contiguous), only when T > P               [P / R3 sub-transforms per thread]
 // with one trip through shared memory between passes; outputs appear at n = n1 + R1 n2 + R1 R2 n3.
+#ifndef OCEAN_FFT_PACKED_3PASS
+#define OCEAN_FFT_PACKED_3PASS 1
+#endif
 template <int N_, int P_>
 struct LineCfg {
     static constexpr int N = N_;
@@ -62,6 +65,9 @@ struct LineCfg {
     static constexpr int SUB3 = P / R3;           // pass-3 sub-transforms per thread (R3 > 1)
     static_assert(R1 * R2 * R3 == N && R3 <= P && (T <= 32 ? 32 % T == 0 : T % 32 == 0), "unsupported factorisation");
     static constexpr int GS = R3 == 1 ? R2 : 32;  // row-group size of the intermediate layout (see Inter)
+    // packed f32x2 butterflies (fft_reg.cuh): the twiddle-free ones for the three-pass lines (N = 2048: +3.5 %
+    // frames/s, bit-identical), scalar elsewhere (1024: -0.5 %, 512: +-0) unless the build overrides it
+    static constexpr int PK = (OCEAN_FFT_PACKED == 0 && R3 > 1) ? OCEAN_FFT_PACKED_3PASS : OCEAN_FFT_PACKED;
     static constexpr int PADQ = T < 32 ? T : 32;
     __host__ __device__ static constexpr int pad(int p) { return p + p / PADQ; }
     // line stride (in float2): >= pad(N-1)+1 and == 2 (mod 16) so that 8 lines x 2 rows of
@@ -87,7 +93,7 @@ __device__ __forceinline__ void line_passes_23(float2* line, int t, const float2
         float2 u[R2];
 #pragma unroll
         for (int k = 0; k < R2; ++k) u[k] = line[Cfg::pad(n1 * T + k * R3 + k3)];
-        RegFft<R2>::run(u);
+        RegFft<R2, Cfg::PK>::run(u);
 #pragma unroll
         for (int n2 = 0; n2 < R2; ++n2)
             line[Cfg::pad(n1 * T + n2 * R3 + k3)] = n2 == 0 ? u[0] : cmul_tw(u[n2], tw2[n2 * R3 + k3]);
@@ -99,7 +105,7 @@ __device__ __forceinline__ void line_passes_23(float2* line, int t, const float2
         float2 w[R3];
 #pragma unroll
         for (int k = 0; k < R3; ++k) w[k] = line[Cfg::pad(n1 * T + n2 * R3 + k)];
-        RegFft<R3>::run(w);
+        RegFft<R3, Cfg::PK>::run(w);
 #pragma unroll
         for (int n3 = 0; n3 < R3; ++n3) out(n1 + R1 * n2 + R1 * R2 * n3, w[n3]);
     }
@@ -125,7 +131,7 @@ __device__ __forceinline__ void line_pass2_shfl(int t, const float2* __restrict_
 #pragma unroll
     for (int k = 0; k < R2; ++k) u[k] = ld(g * T + k * 2 + k3);
     loaded();
-    RegFft<R2>::run(u);
+    RegFft<R2, Cfg::PK>::run(u);
 #pragma unroll
     for (int n2 = 1; n2 < R2; ++n2) u[n2] = cmul_tw(u[n2], tw2[n2 * 2 + k3]);
 #pragma unroll
@@ -182,7 +188,7 @@ __device__ __forceinline__ void rows_line_finish(float2 (&v)[LineCfg<N, P>::R1],
     using IL = Inter<N, C, Cfg::GS>;
     constexpr int T = Cfg::T, R1 = Cfg::R1, R2 = Cfg::R2;
     const bool self_paired = (j == 0);
-    RegFft<R1>::run(v);
+    RegFft<R1, Cfg::PK>::run(v);
 #pragma unroll
     for (int n1 = 0; n1 < R1; ++n1) {
         const float2 y = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * T + k2));
@@ -221,7 +227,7 @@ __device__ __forceinline__ void rows_line_finish(float2 (&v)[LineCfg<N, P>::R1],
         float2 u[R2];
 #pragma unroll
         for (int k = 0; k < R2; ++k) u[k] = line[Cfg::pad(n1 * R2 + k)];
-        RegFft<R2>::run(u);
+        RegFft<R2, Cfg::PK>::run(u);
         const uint32_t col0 = mirrored ? ((N - n1) & (N - 1)) : n1;          // column of n2 = 0
         float2* q = dst + long(col0 / C) * strip_stride + col0 % C;
         if (mirrored && n1 == 0) {
@@ -990,7 +996,7 @@ k_rows_p(const float2* __restrict__ h0_all, const float* __restrict__ omega_all,
         float2 v[R1];
 #pragma unroll
         for (int k1 = 0; k1 < R1; ++k1) v[k1] = line[Cfg::pad(k1 * T + k2)];
-        RegFft<R1>::run(v);
+        RegFft<R1, Cfg::PK>::run(v);
 #pragma unroll
         for (int n1 = 0; n1 < R1; ++n1)          // in place: the slots this thread just read
             line[Cfg::pad(n1 * T + k2)] = n1 == 0 ? v[0] : cmul_tw(v[n1], __ldg(tw_g + n1 * T + k2));
@@ -1025,7 +1031,7 @@ k_rows_p(const float2* __restrict__ h0_all, const float* __restrict__ omega_all,
                 float2 u[R2];
 #pragma unroll
                 for (int k = 0; k < R2; ++k) u[k] = line[Cfg::pad(n1 * R2 + k)];
-                RegFft<R2>::run(u);
+                RegFft<R2, Cfg::PK>::run(u);
                 const uint32_t col0 = mirrored ? ((N - n1) & (N - 1)) : n1;          // column of n2 = 0
                 float2* q = dst + long(col0 / C) * strip_stride + col0 % C;
                 if (mirrored && n1 == 0) {
@@ -1198,7 +1204,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
             }
             ptx::fence_proxy_async();          // this thread's generic reads of GB precede the next bulk copy into it
             ptx::mbar_arrive(emptyG);
-            RegFft<R1>::run(v);
+            RegFft<R1, Cfg::PK>::run(v);
 #pragma unroll
             for (int n1 = 1; n1 < R1; ++n1) v[n1] = cmul_tw(v[n1], TW[n1 * T + k2]);
 #pragma unroll
@@ -1216,7 +1222,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                 }
                 ptx::named_bar_sync<2, NTH>();                          // XH drained: the next item may overwrite it
 #pragma unroll
-                for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2>::run(u[i]);
+                for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2, Cfg::PK>::run(u[i]);
                 ptx::mbar_wait(drainedP + b, (it >> 1) & 1);             // the packed warps hold this item's PB in registers
 #pragma unroll
                 for (int i = 0; i < Cfg::SUB2; ++i) {
@@ -1277,7 +1283,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
             constexpr int K1_STRIDE = (T / Cfg::GS) * IL::GROUP_PITCH;
 #pragma unroll
             for (int k1 = 0; k1 < R1; ++k1) v[k1] = col[k1 * K1_STRIDE];
-            RegFft<R1>::run(v);
+            RegFft<R1, Cfg::PK>::run(v);
 #pragma unroll
             for (int n1 = 0; n1 < R1; ++n1)
                 col[n1 * K1_STRIDE] = n1 == 0 ? v[0] : cmul_tw(v[n1], TW[n1 * T + k2]);
@@ -1308,7 +1314,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                 }
                 ptx::mbar_arrive(drainedP + b);
 #pragma unroll
-                for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2>::run(u[i]);
+                for (int i = 0; i < Cfg::SUB2; ++i) RegFft<R2, Cfg::PK>::run(u[i]);
                 ptx::mbar_wait(hrReady, it & 1);
 #pragma unroll
                 for (int i = 0; i < Cfg::SUB2; ++i) {
@@ -1344,7 +1350,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                     float2 u[R2];
 #pragma unroll
                     for (int k = 0; k < R2; ++k) u[k] = PB[IL::row_off(n1 * T + k * R3 + k3) + c];
-                    RegFft<R2>::run(u);
+                    RegFft<R2, Cfg::PK>::run(u);
 #pragma unroll
                     for (int n2 = 0; n2 < R2; ++n2)
                         PB[IL::row_off(n1 * T + n2 * R3 + k3) + c] = n2 == 0 ? u[0] : cmul_tw(u[n2], TW[N + n2 * R3 + k3]);
@@ -1356,7 +1362,7 @@ k_cols(const float2* __restrict__ gp_all, const float2* __restrict__ gh_all, con
                     const int q = k2 + T * i, n1 = q % R1, n2 = q / R1;
 #pragma unroll
                     for (int k = 0; k < R3; ++k) w[i][k] = PB[IL::row_off(n1 * T + n2 * R3 + k) + c];
-                    RegFft<R3>::run(w[i]);
+                    RegFft<R3, Cfg::PK>::run(w[i]);
                 }
                 ptx::mbar_arrive(drainedP + b);
                 ptx::mbar_wait(hrReady, it & 1);

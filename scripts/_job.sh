@@ -1,8 +1,6 @@
 mkdir -p gpurun_out
-for tool in racecheck; do
-  for cfg in "1024 4 2" "512 3 3" "2048 1 2" "512 3 6 overlapped" "256 2 3" "64 2 3"; do
-    echo "== compute-sanitizer --tool $tool python scripts/san_target.py $cfg"
-    timeout 600 compute-sanitizer --tool $tool --print-limit 6 python scripts/san_target.py $cfg 2>&1 | grep -E "SUMMARY|Error:|access at|checksums|hazards" | cut -c1-330 | head -14
-  done
-done > gpurun_out/r2x_racecheck.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r2z_pytest.log
+python scripts/san_target.py 2048 2 3 > gpurun_out/r2z_sums_2048.log 2>&1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 500 --warmup 10 > gpurun_out/r2z_bench_2gpu.json 2> gpurun_out/r2z_bench_2gpu.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 > gpurun_out/r2z_bench_2gpu_ref.json 2> gpurun_out/r2z_bench_2gpu_ref.err
 echo done

@@ -22,6 +22,11 @@ int main(int argc, char** argv) {
         auto v = o.read_back();
         // SURVEY.md 8c probe at t=1: out[0,0] = (-1.814249, -1.339759, -0.750584)
         std::printf("%.6f %.6f %.6f %.1f\n", v[0], v[1], v[2], v[3]);
+        // the same frame through the lanes of update_overlapped (after a few others): bit-identical map
+        const uint64_t plain = o.checksum();
+        for (int f = 0; f < 5; ++f) o.update_overlapped(0.25f * float(f));
+        o.update_overlapped(1.0f);
+        if (o.checksum() != plain) { std::puts("overlapped update differs"); return 2; }
         return (std::fabs(v[0] + 1.814249f) < 1e-4f && std::fabs(v[1] + 1.339759f) < 1e-4f && v[3] == 0.0f) ? 0 : 1;
     } catch (const OceanError& e) { std::printf("OceanError %d: %s\n", e.status, e.what()); return 3; }
 }
