@@ -335,3 +335,23 @@ def test_overlapped_same_tiles_every_frame_matches_plain():
         assert got.keys() == plain.keys()
         for f in got:
             np.testing.assert_array_equal(got[f], plain[f])
+
+
+@pytest.mark.parametrize("n,tiles,recorded", [
+    (64, 2, [0x492fdbd98f07, 0x498a7a9426d6]),
+    (256, 2, [0x4654c563c6095, 0x46bbf0ef28c41]),
+    (512, 3, [0x123d174b505765, 0x11675d731b6eb6, 0x11ce0c0c35c756]),
+    (1024, 3, [0x46d6504a9e50f6, 0x46aee1b3966151, 0x46ee9539fd5459]),
+    (2048, 2, [0x126bdd7f5985660, 0x120b26594278c21]),
+])
+def test_maps_are_bit_identical_to_the_recorded_round2_maps(n, tiles, recorded):
+    """Checksums of the maps of device-generated tiles (seed 7, stream id = tile) after updates at t = 0, 0.1, 0.2,
+    recorded on B200 before this round's kernel restructuring (batched phase A, per-row mbarriers, shuffle-closed
+    radix-2 and packed butterflies at N = 2048, padded XH / HR): every one of those changes kept the maps bit for bit
+    (scripts/san_target.py prints the same numbers)."""
+    with Ocean(n, 1000.0, n_tiles=tiles) as o:
+        for i in range(tiles):
+            o.generate_spectrum(i, 7, stream_id=i)
+        for f in range(3):
+            o.update(0.1 * f)
+        assert [int(s) for s in o.output_checksums()] == recorded
