@@ -216,7 +216,7 @@ def main():
     import torch
     import torch.distributed as dist
     from gfx_ocean_b200 import FLAG_DOUBLE_BUFFER_OUTPUT, FLAG_DX_PLANE, Ocean, PIPELINE_FUSED, PIPELINE_LITERAL
-    from gfx_ocean_b200.shard import tiles_of_rank
+    from gfx_ocean_b200.shard import fan_out, tiles_of_rank
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -269,7 +269,10 @@ def main():
         """ms for `steps` calls of fn(i), bracketed by barrier + synchronize, max over ranks."""
         barrier()
         ev0.record(stream)
-        for i in range(steps):
+        # launch fan-out, inside the timed region: rank 0 broadcasts the frame block (one NCCL broadcast per `steps`
+        # frames); the frames themselves need no communication
+        first, count, _ = fan_out(0 if rank == 0 else -1, steps if rank == 0 else -1, args.dt, device="cuda")
+        for i in range(first, first + count):
             fn(i)
         ev1.record(stream)
         barrier()

@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from conftest import ROOT
-from gfx_ocean_b200.shard import checksum, rank_of_tile, tiles_of_rank
+from gfx_ocean_b200.shard import checksum, fan_out, rank_of_tile, tiles_of_rank
 
 
 @pytest.mark.parametrize("world,n", [(1, 8), (2, 8), (4, 64), (8, 64), (3, 8), (8, 5), (2, 1)])
@@ -39,9 +39,12 @@ def _worker(rank, world, port, n_tiles, n, q):
     o = COracle()
     o.set_num_threads(1)
     sums = torch.zeros(n_tiles, dtype=torch.float64)
+    # launch fan-out: only rank 0 knows which frames to run; the others learn it from the broadcast block
+    first, count, dt = fan_out(*((4, 1, 0.25) if rank == 0 else (-1, -1, -1.0)))
+    assert (first, count, dt) == (4, 1, 0.25)
     for g in tiles_of_rank(rank, world, n_tiles):          # compute stands in for the GPU frame
         h0, w = synthetic_tile(n, g)
-        sums[g] = checksum(o.frame(h0, w, 1.0, n, prec="f64"))
+        sums[g] = checksum(o.frame(h0, w, first * dt, n, prec="f64"))
     elapsed = torch.tensor([1.0 + rank], dtype=torch.float64)
     dist.all_reduce(sums, op=dist.ReduceOp.SUM)             # control plane only
     dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
@@ -49,6 +52,10 @@ def _worker(rank, world, port, n_tiles, n, q):
     if rank == 0:
         q.put((sums.tolist(), float(elapsed)))
     dist.destroy_process_group()
+
+
+def test_fan_out_is_the_identity_without_a_process_group():
+    assert fan_out(3, 200, 0.016) == (3, 200, 0.016)
 
 
 def test_two_rank_gloo_run_matches_single_rank():
