@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "kernels.h"
@@ -63,9 +64,9 @@ struct ocean_ctx {
     // ocean_update_overlapped: two lanes (stream + own intermediate set), frames alternate between them
     struct Lane {
         cudaStream_t stream = nullptr;
-        cudaEvent_t done = nullptr;       // the lane's latest frame is complete
-        uint32_t first = 0, count = 0;    // its tile range
-        bool busy = false;
+        cudaEvent_t done = nullptr;       // the lane's latest frame (and, by stream order, every earlier one) is complete
+        std::vector<uint8_t> wrote;       // [n_tiles] maps written by frames of this lane that the OTHER lane is not yet ordered behind
+        bool busy = false;                // frames in flight that the main stream is not yet ordered behind
     } lanes[2];
     cudaEvent_t ev_main = nullptr;        // work enqueued on the main stream that the lanes must see (inputs, output routing)
     bool main_dirty = true;               // the main stream saw activity since the lanes last synchronised with it
@@ -145,8 +146,8 @@ int join_lanes(ocean_ctx* c)
     for (auto& l : c->lanes)
         if (l.busy) {
             OCEAN_CUDA(c, cudaStreamWaitEvent(c->stream, l.done, 0));
-            l.busy = false;
-        }
+            l.busy = false;               // (l.wrote stays: the OTHER LANE is still not ordered behind these frames; the
+        }                                 //  lanes only pick the main stream's work up again through ev_main, see below)
     return OCEAN_OK;
 }
 
@@ -579,6 +580,8 @@ int ocean_update_overlapped(ocean_ctx* c, float time, uint32_t first_tile, uint3
         }
         OCEAN_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     }
+    for (auto& l : c->lanes)
+        if (l.wrote.size() != c->n_tiles) l.wrote.assign(c->n_tiles, 0);
     const uint32_t li = c->next_lane;
     auto& L = c->lanes[li];
     auto& O = c->lanes[li ^ 1u];
@@ -588,15 +591,23 @@ int ocean_update_overlapped(ocean_ctx* c, float time, uint32_t first_tile, uint3
         OCEAN_CUDA(c, cudaStreamWaitEvent(c->lanes[0].stream, c->ev_main, 0));
         OCEAN_CUDA(c, cudaStreamWaitEvent(c->lanes[1].stream, c->ev_main, 0));
         c->main_dirty = false;
+        // an entry point that touched the main stream joined both lanes first (OCEAN_ON_DEVICE), so the event just
+        // recorded is behind every frame enqueued so far: both lanes are now ordered behind all of them
+        if (!c->lanes[0].busy && !c->lanes[1].busy)
+            for (auto& l : c->lanes) std::fill(l.wrote.begin(), l.wrote.end(), uint8_t(0));
     }
     // The frame in flight on the other lane uses the other intermediate set, so this frame's row kernel never has to
     // wait for it; only when both frames write the same maps is this frame's COLUMN kernel ordered behind that frame.
-    const bool same_maps = O.busy && first_tile < O.first + O.count && O.first < first_tile + count;
+    // "That frame" is ANY frame of the other lane this lane is not ordered behind yet, not only its latest one: with
+    // disjoint tile ranges the lanes run free of each other, and a later frame of this lane may return to a tile an
+    // older frame of the other lane wrote (O.wrote). O.done is recorded behind all of them (stream order).
+    bool same_maps = false;
+    for (uint32_t t = first_tile; t < first_tile + count && !same_maps; ++t) same_maps = O.wrote[t] != 0;
     if (int rc = enqueue_frame(c, time, first_tile, count, nullptr, nullptr, L.stream, int(li), same_maps ? O.done : nullptr)) return rc;
+    if (same_maps) std::fill(O.wrote.begin(), O.wrote.end(), uint8_t(0));   // this lane's later work is behind O.done now
     OCEAN_CUDA(c, cudaEventRecord(L.done, L.stream));
     L.busy = true;
-    L.first = first_tile;
-    L.count = count;
+    std::fill(L.wrote.begin() + first_tile, L.wrote.begin() + first_tile + count, uint8_t(1));
     c->next_lane = li ^ 1u;
     return OCEAN_OK;
 }

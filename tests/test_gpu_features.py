@@ -355,3 +355,23 @@ def test_maps_are_bit_identical_to_the_recorded_round2_maps(n, tiles, recorded):
         for f in range(3):
             o.update(0.1 * f)
         assert [int(s) for s in o.output_checksums()] == recorded
+
+
+def test_overlapped_frame_returning_to_a_tile_of_an_older_frame_of_the_other_lane():
+    """Lane 0: A (tiles 0..6, long), lane 1: B (tile 7), lane 0: C (tile 7), lane 1: D (tile 0). D returns to a tile that
+    an OLDER frame of lane 0 wrote (lane 0's latest frame, C, does not touch it): D's column kernel must still be
+    ordered behind A, or the long frame A finishes last and leaves its own, older, map in tile 0."""
+    n, tiles = 1024, 8
+    plan = [(0.5, 0, 7), (0.75, 7, 1), (1.0, 7, 1), (1.25, 0, 1)]
+    sums = []
+    for mode in ("plain", "overlapped"):
+        with Ocean(n, 1000.0, n_tiles=tiles) as o:
+            for i in range(tiles):
+                o.generate_spectrum(i, 11, stream_id=i)
+            o.update(0.0)
+            o.sync()
+            for rep in range(20):                                   # the same four frames, back to back
+                for t, first, count in plan:
+                    (o.update_tiles if mode == "plain" else o.update_overlapped)(t + 0.01 * rep, first, count)
+            sums.append(o.output_checksums().copy())
+    np.testing.assert_array_equal(sums[0], sums[1])
