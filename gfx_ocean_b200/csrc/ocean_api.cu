@@ -66,6 +66,7 @@ struct ocean_ctx {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;       // the lane's latest frame (and, by stream order, every earlier one) is complete
         std::vector<uint8_t> wrote;       // [n_tiles] maps written by frames of this lane that the OTHER lane is not yet ordered behind
+        uint32_t first = 0, count = 0;    // tile range of the latest frame (OCEAN_B200_DEBUG_LANES_LATEST only)
         bool busy = false;                // frames in flight that the main stream is not yet ordered behind
     } lanes[2];
     cudaEvent_t ev_main = nullptr;        // work enqueued on the main stream that the lanes must see (inputs, output routing)
@@ -603,11 +604,17 @@ int ocean_update_overlapped(ocean_ctx* c, float time, uint32_t first_tile, uint3
     // older frame of the other lane wrote (O.wrote). O.done is recorded behind all of them (stream order).
     bool same_maps = false;
     for (uint32_t t = first_tile; t < first_tile + count && !same_maps; ++t) same_maps = O.wrote[t] != 0;
+    // hazard hunting: look at the other lane's LATEST frame only (what this entry point first shipped with), to show
+    // that tests/test_gpu_features.py::test_overlapped_frame_returning_to_a_tile_of_an_older_frame_of_the_other_lane sees the gap
+    static const bool latest_only = std::getenv("OCEAN_B200_DEBUG") && std::getenv("OCEAN_B200_DEBUG_LANES_LATEST");
+    if (latest_only) same_maps = O.busy && first_tile < O.first + O.count && O.first < first_tile + count;
     if (int rc = enqueue_frame(c, time, first_tile, count, nullptr, nullptr, L.stream, int(li), same_maps ? O.done : nullptr)) return rc;
     if (same_maps) std::fill(O.wrote.begin(), O.wrote.end(), uint8_t(0));   // this lane's later work is behind O.done now
     OCEAN_CUDA(c, cudaEventRecord(L.done, L.stream));
     L.busy = true;
     std::fill(L.wrote.begin() + first_tile, L.wrote.begin() + first_tile + count, uint8_t(1));
+    L.first = first_tile;
+    L.count = count;
     c->next_lane = li ^ 1u;
     return OCEAN_OK;
 }

@@ -145,8 +145,8 @@ OCEAN_API int  ocean_update_tiles(ocean_ctx* ctx, float time, uint32_t first_til
 OCEAN_API int  ocean_update_graph(ocean_ctx* ctx, float time, uint32_t first_tile, uint32_t count);
 /* ocean_update_tiles with consecutive frames in flight together: calls alternate between two internal lanes (stream +
  * own row-pass intermediate), so the row kernel of one frame runs beside the column kernel of the previous one instead
- * of waiting for it. When both frames write the same maps (same tiles), only this frame's column kernel is ordered
- * behind the other frame. Every other entry point (downloads, sync, plain updates, uploads, ...) first orders the
+ * of waiting for it. When the frame writes a map that a frame still in flight on the other lane wrote (its latest
+ * or an older one), only this frame's column kernel is ordered behind that lane. Every other entry point (downloads, sync, plain updates, uploads, ...) first orders the
  * context's stream behind both lanes -- ocean_join does only that -- so results are those of the same calls made
  * through ocean_update_tiles, bit for bit; a caller that consumes the maps on its own stream calls ocean_join first.
  * FUSED pipeline, single-buffered contexts. */
