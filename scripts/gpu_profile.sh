@@ -27,6 +27,7 @@ for m in tma staged persistent fold; do
   OCEAN_B200_ROWS=$m timeout 300 python bench.py --steps 1000 --no-cpu-baseline --no-extras > gpurun_out/${tag}_rows_${m}.json 2>/dev/null
 done
 timeout 600 python bench.py --total-tiles 64 --steps 200 --no-cpu-baseline --no-extras > gpurun_out/${tag}_bench_64tiles_1xB200.json 2>/dev/null
+# (nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/bulk_latency scripts/ubench/bulk_latency.cu, built before the call)
 if [ -x build/bulk_latency ]; then for m in 0 1 2 3; do ./build/bulk_latency $m; done > gpurun_out/${tag}_bulk_latency.log 2>&1; fi
 for tool in memcheck synccheck racecheck; do
   for cfg in "1024 4 2" "512 3 3" "2048 1 2"; do
