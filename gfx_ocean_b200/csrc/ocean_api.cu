@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "host/lane_order.hpp"
 #include "kernels.h"
 
 struct ocean_ctx {
@@ -65,10 +66,9 @@ struct ocean_ctx {
     struct Lane {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;       // the lane's latest frame (and, by stream order, every earlier one) is complete
-        std::vector<uint8_t> wrote;       // [n_tiles] maps written by frames of this lane that the OTHER lane is not yet ordered behind
         uint32_t first = 0, count = 0;    // tile range of the latest frame (OCEAN_B200_DEBUG_LANES_LATEST only)
-        bool busy = false;                // frames in flight that the main stream is not yet ordered behind
     } lanes[2];
+    ocean::LaneOrder lane_order;          // which column kernels wait for the other lane (host/lane_order.hpp)
     cudaEvent_t ev_main = nullptr;        // work enqueued on the main stream that the lanes must see (inputs, output routing)
     bool main_dirty = true;               // the main stream saw activity since the lanes last synchronised with it
     uint32_t next_lane = 0;
@@ -144,11 +144,9 @@ int join_lanes(ocean_ctx* c);
 // Everything but ocean_update_overlapped runs on the main stream: make it wait for frames still in flight on the lanes.
 int join_lanes(ocean_ctx* c)
 {
-    for (auto& l : c->lanes)
-        if (l.busy) {
-            OCEAN_CUDA(c, cudaStreamWaitEvent(c->stream, l.done, 0));
-            l.busy = false;               // (l.wrote stays: the OTHER LANE is still not ordered behind these frames; the
-        }                                 //  lanes only pick the main stream's work up again through ev_main, see below)
+    for (int i = 0; i < 2; ++i)
+        if (c->lane_order.busy[i]) OCEAN_CUDA(c, cudaStreamWaitEvent(c->stream, c->lanes[i].done, 0));
+    c->lane_order.main_joined();          // (the lanes pick the main stream's work up again through ev_main, see below)
     return OCEAN_OK;
 }
 
@@ -581,8 +579,7 @@ int ocean_update_overlapped(ocean_ctx* c, float time, uint32_t first_tile, uint3
         }
         OCEAN_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     }
-    for (auto& l : c->lanes)
-        if (l.wrote.size() != c->n_tiles) l.wrote.assign(c->n_tiles, 0);
+    c->lane_order.resize(c->n_tiles);
     const uint32_t li = c->next_lane;
     auto& L = c->lanes[li];
     auto& O = c->lanes[li ^ 1u];
@@ -594,25 +591,20 @@ int ocean_update_overlapped(ocean_ctx* c, float time, uint32_t first_tile, uint3
         c->main_dirty = false;
         // an entry point that touched the main stream joined both lanes first (OCEAN_ON_DEVICE), so the event just
         // recorded is behind every frame enqueued so far: both lanes are now ordered behind all of them
-        if (!c->lanes[0].busy && !c->lanes[1].busy)
-            for (auto& l : c->lanes) std::fill(l.wrote.begin(), l.wrote.end(), uint8_t(0));
+        c->lane_order.lanes_resumed();
     }
     // The frame in flight on the other lane uses the other intermediate set, so this frame's row kernel never has to
     // wait for it; only when both frames write the same maps is this frame's COLUMN kernel ordered behind that frame.
-    // "That frame" is ANY frame of the other lane this lane is not ordered behind yet, not only its latest one: with
-    // disjoint tile ranges the lanes run free of each other, and a later frame of this lane may return to a tile an
-    // older frame of the other lane wrote (O.wrote). O.done is recorded behind all of them (stream order).
-    bool same_maps = false;
-    for (uint32_t t = first_tile; t < first_tile + count && !same_maps; ++t) same_maps = O.wrote[t] != 0;
+    // "That frame" is ANY frame of the other lane this lane is not ordered behind yet, not only its latest one
+    // (host/lane_order.hpp). O.done is recorded behind all of them (stream order).
+    static const bool latest_only = std::getenv("OCEAN_B200_DEBUG") && std::getenv("OCEAN_B200_DEBUG_LANES_LATEST");
+    const bool other_busy = c->lane_order.busy[li ^ 1u];
+    bool same_maps = c->lane_order.enqueue(int(li), first_tile, count);
     // hazard hunting: look at the other lane's LATEST frame only (what this entry point first shipped with), to show
     // that tests/test_gpu_features.py::test_overlapped_frame_returning_to_a_tile_of_an_older_frame_of_the_other_lane sees the gap
-    static const bool latest_only = std::getenv("OCEAN_B200_DEBUG") && std::getenv("OCEAN_B200_DEBUG_LANES_LATEST");
-    if (latest_only) same_maps = O.busy && first_tile < O.first + O.count && O.first < first_tile + count;
+    if (latest_only) same_maps = other_busy && first_tile < O.first + O.count && O.first < first_tile + count;
     if (int rc = enqueue_frame(c, time, first_tile, count, nullptr, nullptr, L.stream, int(li), same_maps ? O.done : nullptr)) return rc;
-    if (same_maps) std::fill(O.wrote.begin(), O.wrote.end(), uint8_t(0));   // this lane's later work is behind O.done now
     OCEAN_CUDA(c, cudaEventRecord(L.done, L.stream));
-    L.busy = true;
-    std::fill(L.wrote.begin() + first_tile, L.wrote.begin() + first_tile + count, uint8_t(1));
     L.first = first_tile;
     L.count = count;
     c->next_lane = li ^ 1u;
